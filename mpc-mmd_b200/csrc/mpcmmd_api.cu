@@ -1,0 +1,405 @@
+// mpcmmd_api.cu -- C ABI of libmpcmmd.so (see include/mpcmmd.h): handle lifetime, the batched
+// solve (one CUDA graph of 2 + 3*maxiter_cem kernels per (cost kind, episode count)) and the
+// stage entry points used by the teacher-forced parity tests.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/mpcmmd.h"
+#include "k_project.cuh"
+#include "k_risk.cuh"
+#include "k_select.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" const char* mpcmmd_last_error(void) { return g_err.c_str(); }
+extern "C" int mpcmmd_version(void) { return 100; }
+
+struct mpcmmd_handle_s {
+    int device = 0;
+    mpcmmd_config cfg;         // host copy (matrix pointers are NOT valid after create)
+    DCfg d;
+    DWork w;
+    float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
+    int E = 0;
+    std::vector<void*> allocs;
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    int last_launches = 0;
+    cudaStream_t own_stream = nullptr;
+};
+
+template <typename Tp>
+static int dalloc(mpcmmd_handle_s* h, Tp** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, (n ? n : 1) * sizeof(Tp)));
+    CK(cudaMemset(q, 0, (n ? n : 1) * sizeof(Tp)));
+    h->allocs.push_back(q);
+    *p = (Tp*)q;
+    return 0;
+}
+static int upload(mpcmmd_handle_s* h, const float** dst, const float* src, size_t n) {
+    if (!src) return fail("mpcmmd_create: null matrix pointer in config");
+    float* q = nullptr;
+    if (dalloc(h, &q, n)) return -1;
+    CK(cudaMemcpy(q, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    *dst = q;
+    return 0;
+}
+
+// k_init also prepares the per-episode boundary vectors (cem_helper.py:152-167, cem.py:218-219)
+__global__ void k_boundary(const float* init_state, float* beq_x, float* beq_y, float* state0, int n_ep) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ep) return;
+    const float* s = init_state + e * 6;    // x, y, vx, vy, ax, ay
+    beq_x[e * 3 + 0] = s[0]; beq_x[e * 3 + 1] = s[2]; beq_x[e * 3 + 2] = s[4];
+    beq_y[e * 4 + 0] = s[1]; beq_y[e * 4 + 1] = s[3]; beq_y[e * 4 + 2] = s[5]; beq_y[e * 4 + 3] = 0.0f;
+    state0[e * 5 + 0] = s[0]; state0[e * 5 + 1] = s[1]; state0[e * 5 + 2] = s[2]; state0[e * 5 + 3] = s[3];
+    state0[e * 5 + 4] = dm::atan2_(s[3], s[2]);
+}
+
+static size_t risk_opt_smem(const DCfg& d) { return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float); }
+static size_t risk_base_smem(const DCfg& d) { return (size_t)RISKB_WARPS * riskb_warp_floats(d.nr, d.np) * sizeof(float); }
+
+typedef void (*risk_opt_fn)(DCfg, RiskArgs);
+static risk_opt_fn pick_risk_opt(int nr) {
+    switch (nr) {
+        case 2: return k_risk_opt<2>;
+        case 3: return k_risk_opt<3>;
+        case 4: return k_risk_opt<4>;
+        case 5: return k_risk_opt<5>;
+        case 6: return k_risk_opt<6>;
+        case 8: return k_risk_opt<8>;
+        case 10: return k_risk_opt<10>;
+        default: return nullptr;
+    }
+}
+
+extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle* out) {
+    if (!cfg || !out) return fail("mpcmmd_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mpcmmd_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("mpcmmd_create: bad device index");
+    CK(cudaSetDevice(device));
+    const int B = cfg->num_batch, np = cfg->num_prime, nr = cfg->num_reduced, nm = nr * nr, E = cfg->max_episodes;
+    if (B < cfg->ellite_num_cost || cfg->ellite_num_cost > 32 || cfg->ellite_num > 8 || cfg->ellite_num > cfg->ellite_num_cost)
+        return fail("mpcmmd_create: need ellite_num <= 8, ellite_num <= ellite_num_cost <= min(32, num_batch)");
+    if (np < 2 || np > MPCMMD_T) return fail("mpcmmd_create: num_prime must be in [2,100]");
+    if (nr < 2 || nr > MPCMMD_MAX_NR) return fail("mpcmmd_create: num_reduced must be in [2,10]");
+    if (cfg->num_obs < 1 || E < 1) return fail("mpcmmd_create: num_obs and max_episodes must be >= 1");
+    if (cfg->num_samples_cem > RISKO_THREADS * 8 || cfg->num_ellite_beta < 2 || cfg->num_ellite_beta >= cfg->num_samples_cem)
+        return fail("mpcmmd_create: bad inner-CEM sizes");
+    if (cfg->maxiter_beta_cem > 64 || cfg->maxiter_beta_cem > SEL_THREADS) return fail("mpcmmd_create: maxiter_beta_cem too large");
+    mpcmmd_handle_s* h = new mpcmmd_handle_s();
+    h->device = device; h->cfg = *cfg; h->E = E;
+    DCfg& d = h->d;
+    d.B = B; d.np = np; d.nr = nr; d.nm = nm; d.O = cfg->num_obs; d.iters = cfg->maxiter_cem; d.n_el = cfg->ellite_num;
+    d.n_el_cost = cfg->ellite_num_cost; d.noise_kind = cfg->noise_kind; d.S_in = cfg->num_samples_cem; d.iters_in = cfg->maxiter_beta_cem;
+    d.n_el_in = cfg->num_ellite_beta;
+    d.sigma_acc = cfg->sigma_acc; d.sigma_steer = cfg->sigma_steer; d.ksig_steer = cfg->ksig_steer; d.acc_const = cfg->acc_const_noise;
+    d.steer_const = cfg->steer_const_noise; d.beta_a = cfg->beta_a; d.beta_b = cfg->beta_b;
+    d.v_min = cfg->v_min; d.v_max = cfg->v_max; d.a_max = cfg->a_max;
+    d.b_lane_ub = 1.0f * cfg->y_ub; d.b_lane_lb = -1.0f * cfg->y_lb;         // projection.py:127-128, gamma = 1
+    d.y_lb = cfg->y_lb; d.y_ub = cfg->y_ub; d.a2_obs = cfg->a_obs_sq; d.b2_obs = cfg->b_obs_sq;
+    d.wheel_base = cfg->wheel_base; d.dt = cfg->dt; d.steer_max = cfg->steer_max; d.steer_rate_pen = cfg->steer_rate_pen;
+    d.alpha_quant = cfg->alpha_quant; d.ker_wt = cfg->ker_wt; d.lam_inv = cfg->lamda_inv;
+    d.one_m_alpha_mean = cfg->one_minus_alpha_mean; d.alpha_mean = cfg->alpha_mean;
+    d.one_m_alpha_cov = cfg->one_minus_alpha_cov; d.alpha_cov = cfg->alpha_cov;
+    d.sigma_clip = cfg->sigma_clip; d.inv_nm = (float)(1.0 / nm); d.m2_inv_nm = (float)(-2.0 * (1.0 / nm)); d.beta_del = (float)(1.0 / nr);
+    d.sigma_random = cfg->sigma_random;
+#define UP(dst, src, n) if (upload(h, &d.dst, cfg->src, (n))) { mpcmmd_destroy(h); return -1; }
+    UP(P, P, 1100) UP(Pd, Pdot, 1100) UP(Pdd, Pddot, 1100) UP(Gx, Gx, 77) UP(Gy, Gy, 88) UP(Kx, Kx, 154) UP(Ky, Ky, 165) UP(Wfit, Wfit, (size_t)NV * np)
+#undef UP
+    DWork& w = h->w;
+    const size_t EB = (size_t)E * B, n = (size_t)nr * np, ncem = (size_t)(B - d.n_el) * NPAR;
+#define AL(p, cnt) if (dalloc(h, &w.p, (cnt))) { mpcmmd_destroy(h); return -1; }
+    AL(params, EB * NPAR) AL(lam_x, EB * NV) AL(lam_y, EB * NV) AL(s_lane, EB * 2 * NL) AL(mean, (size_t)E * NPAR) AL(cov, (size_t)E * 64)
+    AL(cx, EB * NV) AL(cy, EB * NV) AL(res_norm, EB) AL(cost_base, EB) AL(acc, EB * T_) AL(steer, EB * T_) AL(risk, EB) AL(lane, EB)
+    AL(beta, EB * nr) AL(sigma, EB) AL(res_beta, EB * d.iters_in)
+    AL(z1, (size_t)E * d.iters * n) AL(z2, (size_t)E * d.iters * n) AL(z3, (size_t)E * d.iters * n) AL(zcem, (size_t)E * d.iters * ncem)
+    AL(keys, (size_t)E * d.iters * 4)
+    AL(idx_mpc, E) AL(init_state, (size_t)E * 6) AL(mean0, (size_t)E * NPAR) AL(cov0, (size_t)E * 64)
+    AL(x_obs, (size_t)E * d.O * T_) AL(y_obs, (size_t)E * d.O * T_) AL(v_des, E)
+    AL(o_cx, (size_t)E * NV) AL(o_cy, (size_t)E * NV) AL(o_lane, E) AL(o_obs, E) AL(o_beta, (size_t)E * nr) AL(o_sigma, E)
+    AL(o_res_beta, (size_t)E * d.iters_in) AL(o_sel, (size_t)E * d.iters)
+#undef AL
+    if (dalloc(h, &h->beq_x, (size_t)E * 3) || dalloc(h, &h->beq_y, (size_t)E * 4) || dalloc(h, &h->state0, (size_t)E * 5)) { mpcmmd_destroy(h); return -1; }
+    // constant normal tables [survey Q8]: every key below derives from PRNGKey(0) only
+    {
+        const int S = d.S_in, dd = nm + 1, ne = d.n_el_in;
+        float *z_init, *theta0, *zb, *ztmp;
+        if (dalloc(h, &z_init, (size_t)B * NPAR) || dalloc(h, &theta0, (size_t)S * dd) || dalloc(h, &zb, (size_t)d.iters_in * (S - ne) * dd) ||
+            dalloc(h, &ztmp, (size_t)S * dd)) { mpcmmd_destroy(h); return -1; }
+        // host-side key derivation mirrors the device functions (integer-only Threefry)
+        auto tf = [](uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o) {
+            auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+            const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+            uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+            x0 += ks[0]; x1 += ks[1];
+            for (int i = 0; i < 5; i++) {
+                for (int r = 0; r < 4; r++) { x0 += x1; x1 = rotl(x1, R[i & 1][r]); x1 ^= x0; }
+                x0 += ks[(i + 1) % 3]; x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+            }
+            o[0] = x0; o[1] = x1;
+        };
+        auto split0 = [&](uint32_t* k) { uint32_t a[2], b[2]; tf(k[0], k[1], 0u, 2u, a); tf(k[0], k[1], 1u, 3u, b); k[0] = a[0]; k[1] = b[0]; };
+        uint32_t key_init[2] = {0u, 0u};
+        split0(key_init);                                                         // cem_helper.py:125 / compute_beta.py:108
+        k_normal_table<<<64, 256>>>(key_init[0], key_init[1], B * NPAR, z_init);
+        uint32_t kk[2] = {key_init[0], key_init[1]};
+        split0(kk);                                                               // compute_beta.py:44
+        k_normal_table<<<64, 256>>>(kk[0], kk[1], S * dd, ztmp);
+        k_theta0<<<64, 256>>>(ztmp, S, dd, d.sigma_clip, theta0);
+        uint32_t carry[2] = {key_init[0], key_init[1]};
+        for (int it = 0; it < d.iters_in; it++) {
+            split0(carry);                                                        // compute_beta.py:131
+            uint32_t dk[2] = {carry[0], carry[1]};
+            split0(dk);                                                           // compute_beta.py:54
+            k_normal_table<<<64, 256>>>(dk[0], dk[1], (S - ne) * dd, zb + (size_t)it * (S - ne) * dd);
+        }
+        d.z_init = z_init; d.theta0 = theta0; d.zb_iter = zb;
+    }
+    // opt-in shared memory sizes
+    if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
+    if (risk_base_smem(d) > 48 * 1024 && cudaFuncSetAttribute(k_risk_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)risk_base_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_risk_base smem opt-in failed"); }
+    risk_opt_fn f = pick_risk_opt(nr);
+    if (f) {
+        if (risk_opt_smem(d) > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)risk_opt_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_risk_opt smem opt-in failed"); }
+    }
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    *out = h;
+    return 0;
+}
+
+extern "C" int mpcmmd_destroy(mpcmmd_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+static float w_obs_for(const mpcmmd_handle_s* h, int kind) { (void)h; return kind == MPCMMD_COST_SAA ? 1.0e6f : 1.0e3f; }   // cem.py:161-163
+
+static ProjArgs proj_args(mpcmmd_handle_s* h, int n_ep) {
+    ProjArgs p;
+    p.n_samples = n_ep * h->d.B; p.B = h->d.B; p.params = h->w.params; p.beq_x = h->beq_x; p.beq_y = h->beq_y; p.v_des = h->w.v_des;
+    p.lam_x = h->w.lam_x; p.lam_y = h->w.lam_y; p.s_lane = h->w.s_lane; p.cx = h->w.cx; p.cy = h->w.cy; p.res_norm = h->w.res_norm;
+    p.cost_base = h->w.cost_base; p.acc = h->w.acc; p.steer = h->w.steer;
+    return p;
+}
+static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s) {
+    const int blocks = (p.n_samples + PROJ_WARPS - 1) / PROJ_WARPS;
+    k_project<<<blocks, PROJ_WARPS * 32, PROJ_SMEM_BYTES, s>>>(h->d, p);
+    return 0;
+}
+static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s) {
+    if (r.cost_kind == MPCMMD_COST_MMD_OPT) {
+        risk_opt_fn f = pick_risk_opt(h->d.nr);
+        if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
+        f<<<r.n_samples, RISKO_THREADS, risk_opt_smem(h->d), s>>>(h->d, r);
+    } else {
+        const int blocks = (r.n_samples + RISKB_WARPS - 1) / RISKB_WARPS;
+        k_risk_base<<<blocks, RISKB_WARPS * 32, risk_base_smem(h->d), s>>>(h->d, r);
+    }
+    return 0;
+}
+
+// enqueue the whole solve on `s` (captured into a graph by the caller)
+static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s, int* launches) {
+    const DCfg& d = h->d; DWork& w = h->w;
+    const size_t n = (size_t)d.nr * d.np, ncem = (size_t)(d.B - d.n_el) * NPAR;
+    int cnt = 0;
+    k_boundary<<<(n_ep + 127) / 128, 128, 0, s>>>(w.init_state, h->beq_x, h->beq_y, h->state0, n_ep); cnt++;
+    k_noise<<<n_ep * d.iters, 128, 0, s>>>(d, w, n_ep, 0, d.iters); cnt++;
+    k_init<<<n_ep, 128, 0, s>>>(d, w, n_ep); cnt++;
+    for (int it = 0; it < d.iters; it++) {
+        ProjArgs p = proj_args(h, n_ep);
+        launch_project(h, p, s); cnt++;
+        RiskArgs r;
+        r.n_samples = n_ep * d.B; r.B = d.B; r.cost_kind = kind; r.acc = w.acc; r.steer = w.steer; r.state0 = h->state0;
+        r.z1 = w.z1 + it * n; r.z2 = w.z2 + it * n; r.z3 = w.z3 + it * n; r.z_stride = (size_t)d.iters * n;
+        r.keys = w.keys + it * 4; r.key_stride = (size_t)d.iters * 4;
+        r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
+        if (launch_risk(h, r, s)) return -1;
+        cnt++;
+        SelArgs a;
+        a.n_ep = n_ep; a.B = d.B; a.it = it; a.nr = d.nr; a.iters_in = d.iters_in; a.w_obs = w_obs_for(h, kind);
+        a.res_norm = w.res_norm; a.risk = w.risk; a.lane = w.lane; a.cost_base = w.cost_base; a.params = w.params; a.mean = w.mean; a.cov = w.cov;
+        a.zcem = w.zcem + it * ncem; a.z_stride = (size_t)d.iters * ncem; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma;
+        a.res_beta = w.res_beta; a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta;
+        a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta; a.o_sel = w.o_sel; a.sel_stride = d.iters;
+        k_select<<<n_ep, SEL_THREADS, 2 * d.B * sizeof(float), s>>>(d, a); cnt++;
+    }
+    *launches = cnt;
+    return 0;
+}
+
+static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
+    auto key = std::make_pair(kind, n_ep);
+    auto it = h->graphs.find(key);
+    if (it != h->graphs.end()) { *out = it->second; h->last_launches = 3 + 3 * h->d.iters; return 0; }
+    cudaGraph_t g;
+    int launches = 0;
+    CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_solve(h, kind, n_ep, h->own_stream, &launches);
+    cudaError_t ce = cudaStreamEndCapture(h->own_stream, &g);
+    if (rc) return -1;
+    CK(ce);
+    cudaGraphExec_t ge;
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    h->graphs[key] = ge;
+    h->last_launches = launches;
+    *out = ge;
+    return 0;
+}
+
+static int check_solve_args(mpcmmd_handle_s* h, int kind, int n_ep) {
+    if (!h) return fail("null handle");
+    if (kind < 0 || kind > 3) return fail("mpcmmd_solve: bad cost kind");
+    if (n_ep < 1 || n_ep > h->E) return fail("mpcmmd_solve: n_ep outside [1, max_episodes]");
+    if (2 * (size_t)h->d.B * sizeof(float) > 48 * 1024) return fail("mpcmmd_solve: num_batch too large for k_select");
+    return 0;
+}
+
+static int solve_impl(mpcmmd_handle_s* h, int kind, int n_ep, const int32_t* idx_mpc, const float* init_state, const float* mean,
+                      const float* cov, const float* x_obs, const float* y_obs, const float* v_des, const mpcmmd_out* out,
+                      cudaStream_t s, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+    if (check_solve_args(h, kind, n_ep)) return -1;
+    if (!idx_mpc || !init_state || !mean || !cov || !x_obs || !y_obs || !v_des || !out) return fail("mpcmmd_solve: null pointer");
+    CK(cudaSetDevice(h->device));
+    const DCfg& d = h->d; DWork& w = h->w;
+    cudaGraphExec_t ge;
+    if (get_graph(h, kind, n_ep, &ge)) return -1;
+    CK(cudaMemcpyAsync(w.idx_mpc, idx_mpc, sizeof(int32_t) * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.init_state, init_state, sizeof(float) * 6 * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.mean0, mean, sizeof(float) * NPAR * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.cov0, cov, sizeof(float) * 64 * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.x_obs, x_obs, sizeof(float) * d.O * T_ * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.y_obs, y_obs, sizeof(float) * d.O * T_ * n_ep, in_kind, s));
+    CK(cudaMemcpyAsync(w.v_des, v_des, sizeof(float) * n_ep, in_kind, s));
+    CK(cudaGraphLaunch(ge, s));
+    if (out->cx) CK(cudaMemcpyAsync(out->cx, w.o_cx, sizeof(float) * NV * n_ep, out_kind, s));
+    if (out->cy) CK(cudaMemcpyAsync(out->cy, w.o_cy, sizeof(float) * NV * n_ep, out_kind, s));
+    if (out->cost_lane) CK(cudaMemcpyAsync(out->cost_lane, w.o_lane, sizeof(float) * n_ep, out_kind, s));
+    if (out->cost_obs) CK(cudaMemcpyAsync(out->cost_obs, w.o_obs, sizeof(float) * n_ep, out_kind, s));
+    if (out->beta) CK(cudaMemcpyAsync(out->beta, w.o_beta, sizeof(float) * d.nr * n_ep, out_kind, s));
+    if (out->sigma) CK(cudaMemcpyAsync(out->sigma, w.o_sigma, sizeof(float) * n_ep, out_kind, s));
+    if (out->res_beta) CK(cudaMemcpyAsync(out->res_beta, w.o_res_beta, sizeof(float) * d.iters_in * n_ep, out_kind, s));
+    return 0;
+}
+
+extern "C" int mpcmmd_solve(mpcmmd_handle h, int cost_kind, int n_ep, const int32_t* idx_mpc, const float* init_state, const float* mean,
+                            const float* cov, const float* x_obs, const float* y_obs, const float* v_des, const mpcmmd_out* out, void* stream) {
+    return solve_impl(h, cost_kind, n_ep, idx_mpc, init_state, mean, cov, x_obs, y_obs, v_des, out, (cudaStream_t)stream,
+                      cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+}
+extern "C" int mpcmmd_solve_host(mpcmmd_handle h, int cost_kind, int n_ep, const int32_t* idx_mpc, const float* init_state, const float* mean,
+                                 const float* cov, const float* x_obs, const float* y_obs, const float* v_des, const mpcmmd_out* out) {
+    if (!h) return fail("null handle");
+    if (solve_impl(h, cost_kind, n_ep, idx_mpc, init_state, mean, cov, x_obs, y_obs, v_des, out, h->own_stream,
+                   cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost)) return -1;
+    CK(cudaStreamSynchronize(h->own_stream));
+    return 0;
+}
+extern "C" int mpcmmd_last_launch_count(mpcmmd_handle h) { return h ? h->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// stage entry points (synchronous, default stream)
+
+extern "C" int mpcmmd_math_vec(int fn, const float* x, const float* y, float* out, int n, int device) {
+    CK(cudaSetDevice(device));
+    k_math_vec<<<(n + 255) / 256, 256>>>(fn, x, y ? y : x, out, n);
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_rng_normal(uint32_t k0, uint32_t k1, int n, float* out, int device) {
+    CK(cudaSetDevice(device));
+    k_normal_table<<<(n + 255) / 256, 256>>>(k0, k1, n, out);
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_rng_beta(uint32_t k0, uint32_t k1, const float* a, const float* b, int n, float* out, int device) {
+    CK(cudaSetDevice(device));
+    k_beta_table<<<(n + 127) / 128, 128>>>(k0, k1, a, b, n, out);
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_get_tables(mpcmmd_handle h, float* z_init, float* theta0, float* zb_iter) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    const DCfg& d = h->d; const int dd = d.nm + 1;
+    if (z_init) CK(cudaMemcpy(z_init, d.z_init, sizeof(float) * d.B * NPAR, cudaMemcpyDeviceToDevice));
+    if (theta0) CK(cudaMemcpy(theta0, d.theta0, sizeof(float) * d.S_in * dd, cudaMemcpyDeviceToDevice));
+    if (zb_iter) CK(cudaMemcpy(zb_iter, d.zb_iter, sizeof(float) * d.iters_in * (d.S_in - d.n_el_in) * dd, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+extern "C" int mpcmmd_stage_project(mpcmmd_handle h, int n, const float* params, const float* beq_x, const float* beq_y, float v_des,
+                                    float* lam_x, float* lam_y, float* s_lane, float* cx, float* cy, float* res_norm, float* acc, float* steer,
+                                    float* cost_base) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    float* vd = h->w.v_des;                     // one "episode": sample g -> e = g / n = 0
+    CK(cudaMemcpy(vd, &v_des, sizeof(float), cudaMemcpyHostToDevice));
+    ProjArgs p;
+    p.n_samples = n; p.B = n; p.params = params; p.beq_x = beq_x; p.beq_y = beq_y; p.v_des = vd; p.lam_x = lam_x; p.lam_y = lam_y; p.s_lane = s_lane;
+    p.cx = cx; p.cy = cy; p.res_norm = res_norm; p.cost_base = cost_base; p.acc = acc; p.steer = steer;
+    launch_project(h, p, 0);
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const float* acc, const float* steer, const float* state0,
+                                 const float* z1, const float* z2, const float* z3, const uint32_t* keys, const float* x_obs, const float* y_obs,
+                                 float* risk, float* lane, float* beta, float* sigma, float* res_beta) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    RiskArgs r;
+    r.n_samples = n; r.B = n; r.cost_kind = cost_kind; r.acc = acc; r.steer = steer; r.state0 = state0; r.z1 = z1; r.z2 = z2; r.z3 = z3; r.z_stride = 0;
+    r.keys = keys; r.key_stride = 0; r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
+    if (launch_risk(h, r, 0)) return -1;
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float* res_norm, const float* risk, const float* cost_base, float* params,
+                                   float* mean, float* cov, const float* z_cem, int32_t* sel) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    const DCfg& d = h->d; DWork& w = h->w;
+    SelArgs a;
+    a.n_ep = 1; a.B = d.B; a.it = 0; a.nr = d.nr; a.iters_in = d.iters_in; a.w_obs = w_obs_for(h, cost_kind);
+    a.res_norm = res_norm; a.risk = risk; a.lane = w.lane; a.cost_base = cost_base; a.params = params; a.mean = mean; a.cov = cov;
+    a.zcem = z_cem; a.z_stride = 0; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma; a.res_beta = w.res_beta;
+    a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta; a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta;
+    a.o_sel = sel; a.sel_stride = 1;
+    k_select<<<1, SEL_THREADS, 2 * d.B * sizeof(float)>>>(d, a);
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int mpcmmd_stage_noise(mpcmmd_handle h, int32_t idx_mpc, int32_t iter, float* z1, float* z2, float* z3, float* z_cem, uint32_t* keys) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    const DCfg& d = h->d; DWork& w = h->w;
+    if (iter < 0 || iter >= d.iters) return fail("mpcmmd_stage_noise: iter outside [0, maxiter_cem)");
+    const size_t n = (size_t)d.nr * d.np, ncem = (size_t)(d.B - d.n_el) * NPAR;
+    CK(cudaMemcpy(w.idx_mpc, &idx_mpc, sizeof(int32_t), cudaMemcpyHostToDevice));
+    DCfg dg = d; dg.noise_kind = 0;                                  // always emit the Gaussian tables here
+    k_noise<<<1, 128>>>(dg, w, 1, iter, 1);
+    CK(cudaDeviceSynchronize());
+    const size_t slot = (size_t)iter;
+    if (z1) CK(cudaMemcpy(z1, w.z1 + slot * n, sizeof(float) * n, cudaMemcpyDeviceToDevice));
+    if (z2) CK(cudaMemcpy(z2, w.z2 + slot * n, sizeof(float) * n, cudaMemcpyDeviceToDevice));
+    if (z3) CK(cudaMemcpy(z3, w.z3 + slot * n, sizeof(float) * n, cudaMemcpyDeviceToDevice));
+    if (z_cem) CK(cudaMemcpy(z_cem, w.zcem + slot * ncem, sizeof(float) * ncem, cudaMemcpyDeviceToDevice));
+    if (keys) CK(cudaMemcpy(keys, w.keys + slot * 4, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
+    return 0;
+}

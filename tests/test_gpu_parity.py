@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, BIT EXACT.
+
+The arithmetic contract makes every float32 result reproducible, so the bar
+here is `np.array_equal`, which is stricter than the 1e-4 relative tolerance north_star asks for
+(and implies identical elite index sets and identical downstream collision counts)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _eq(a, b, what=""):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b, equal_nan=True):
+        bad = np.flatnonzero(~((a == b) | (np.isnan(a) & np.isnan(b))).ravel())
+        raise AssertionError(f"{what}: {bad.size}/{a.size} elements differ; first at {bad[:5]}: got {a.ravel()[bad[:5]]} want {b.ravel()[bad[:5]]}")
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mpcmmd_b200 import cem_impl
+    from oracle import oracle as O
+    return cem_impl, O
+
+
+MATH_RANGES = {"exp": (-100.0, 90.0), "log": (1e-42, 1e6), "log1p": (-0.9999999, 10.0), "sin": (-700.0, 700.0), "cos": (-700.0, 700.0),
+               "tan": (-1.6, 1.6), "atan": (-1e4, 1e4), "erfinv": (-0.99999994, 0.99999994)}
+
+
+@pytest.mark.parametrize("fn", list(MATH_RANGES))
+def test_device_math_bit_exact(mods, fn):
+    cem_impl, O = mods
+    rng = np.random.default_rng(1)
+    lo, hi = MATH_RANGES[fn]
+    x = rng.uniform(lo, hi, 400000).astype(f32)
+    if fn == "log":
+        x = np.concatenate([x, np.exp(rng.uniform(-95, 20, 200000)).astype(f32), [0.0, np.inf]]).astype(f32)
+    if fn in ("sin", "cos"):
+        x = np.concatenate([x, rng.uniform(-7, 7, 400000).astype(f32)])
+    x = np.concatenate([x, np.array([0.0, -0.0, np.nan], f32)])
+    _eq(cem_impl.math_vec(O.MATH_FN[fn], x), O.math_vec(fn, x), fn)
+    if fn == "exp":      # the hot-loop variant on its domain
+        xn = x[(x <= 0) | np.isnan(x)]
+        _eq(cem_impl.math_vec(9, xn), O.math_vec("exp", xn), "exp_nonpos")
+    if fn == "sin":
+        _eq(cem_impl.math_vec(10, x), O.math_vec("sin", x), "sincos.s")
+    if fn == "cos":
+        _eq(cem_impl.math_vec(11, x), O.math_vec("cos", x), "sincos.c")
+
+
+def test_device_atan2_bit_exact(mods):
+    cem_impl, O = mods
+    rng = np.random.default_rng(2)
+    x = rng.normal(0, 10, 300000).astype(f32); y = rng.normal(0, 10, 300000).astype(f32)
+    x[:100] = 0.0; y[50:150] = 0.0
+    _eq(cem_impl.math_vec(7, x, y), O.math_vec("atan2", x, y), "atan2")
+
+
+def test_device_rng_normal_matches_known_answers(mods):
+    cem_impl, O = mods
+    got = cem_impl.rng_normal((0, 0), 1)
+    assert abs(float(got[0]) - (-0.20584226)) < 2e-7          # jax.random.normal(PRNGKey(0), (1,)) from the JAX docs
+    for key, n in (((0, 0), 1), ((0, 42), 7), ((123, 456), 800), ((4146024105, 967050713), 2501)):
+        _eq(cem_impl.rng_normal(key, n), O.normal(key, n), f"normal{key}")
+
+
+def test_device_rng_beta_bit_exact(mods):
+    cem_impl, O = mods
+    rng = np.random.default_rng(3)
+    a = np.abs(rng.normal(0, 2, 3000)).astype(f32) * 2; b = a * f32(2.5)
+    a[:5] = 0.0; b[:5] = 0.0                                   # alpha = 0 edge (acc[99] = 0 in the reference)
+    a[5:10] = 1e-6; b[5:10] = 2.5e-6
+    got = cem_impl.rng_beta((7, 9), a, b); want = O.beta((7, 9), a, b)
+    _eq(got, want, "beta")
+    ok = ~np.isnan(want)
+    assert ok.sum() > 2900 and np.all((want[ok] >= 0) & (want[ok] <= 1))
+
+
+SMALL = dict(num_batch=24, maxiter_cem=3, num_samples_cem=40, maxiter_beta_cem=4)
+
+
+def _pair(mods, args, variant="static", **kw):
+    cem_impl, O = mods
+    return cem_impl.CEM(*args, variant=variant, max_episodes=kw.pop("max_episodes", 4), **kw), O.OracleCEM(*args, variant=variant, **kw)
+
+
+def test_constant_tables_bit_exact(mods):
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0))
+    zi, th, zb = prob.tables()
+    _eq(zi, ora.z_init, "z_init"); _eq(th, ora.theta0, "theta0"); _eq(zb, ora.zb_iter, "zb_iter")
+
+
+@pytest.mark.parametrize("variant", ["static", "dynamic"])
+def test_stage_project_bit_exact(mods, variant):
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), variant=variant)
+    rng = np.random.default_rng(5)
+    n = 37
+    params = np.concatenate([rng.uniform(0.1, 30, (n, 4)), rng.normal(0, 6, (n, 4))], 1).astype(f32)
+    beq_x = np.array([0.0, 5.0, 0.3], f32); beq_y = np.array([1.75 if variant == "static" else -1.75, 0.2, -0.1, 0.0], f32)
+    lam_x = rng.normal(0, 0.5, (n, 11)).astype(f32); lam_y = rng.normal(0, 0.5, (n, 11)).astype(f32)
+    s_lane = np.abs(rng.normal(0, 1, (n, 198))).astype(f32)
+    lam_x[:10] = 0; lam_y[:10] = 0; s_lane[:10] = 0
+    got = prob.stage_project(params, beq_x, beq_y, 15.0, lam_x, lam_y, s_lane)
+    for i in range(n):
+        lx, ly, sl = lam_x[i].copy(), lam_y[i].copy(), s_lane[i].copy()
+        ref = ora.project(params[i], beq_x, beq_y, 15.0, lx, ly, sl)
+        for k in ("cx", "cy", "res_norm", "acc", "steer", "cost_base"):
+            _eq(got[k][i], ref[k], f"project[{i}].{k}")
+        _eq(got["lam_x"][i], lx, "lam_x"); _eq(got["lam_y"][i], ly, "lam_y"); _eq(got["s_lane"][i], sl, "s_lane")
+
+
+def test_stage_noise_bit_exact(mods):
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0))
+    for idx_mpc, it in ((6745, 0), (1, 19), (9999, 7)):
+        g = prob.stage_noise(idx_mpc, it); r = ora.noise_tables(idx_mpc, it)
+        for a, b, nm in zip(g[:4], r[:4], ("z1", "z2", "z3", "zcem")):
+            _eq(a, b, nm)
+        assert list(g[4]) == list(r[4])
+
+
+def _controls(ora, rng, n):
+    out = []
+    beq_x = np.array([0.0, 5.0, 0.0], f32); beq_y = np.array([1.75, 0.0, 0.0, 0.0], f32)
+    for _ in range(n):
+        p = np.concatenate([rng.uniform(2, 25, 4), rng.normal(0, 3, 4)]).astype(f32)
+        o = ora.project(p, beq_x, beq_y, 15.0, np.zeros(11, f32), np.zeros(11, f32), np.zeros(198, f32))
+        out.append((o["acc"], o["steer"]))
+    return np.stack([a for a, _ in out]), np.stack([s for _, s in out])
+
+
+@pytest.mark.parametrize("cost,noise,nr,npr,nobs", [
+    ("cvar", "gaussian", 5, 30, 2), ("cvar", "beta", 5, 50, 4), ("saa", "gaussian", 4, 20, 3), ("mmd_random", "gaussian", 5, 30, 2),
+    ("mmd_opt", "gaussian", 5, 30, 2), ("mmd_opt", "beta", 3, 20, 2), ("mmd_opt", "gaussian", 10, 40, 3), ("cvar", "gaussian", 10, 100, 6)])
+def test_stage_risk_bit_exact(mods, cost, noise, nr, npr, nobs):
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=4) if cost == "mmd_opt" else {}
+    prob, ora = _pair(mods, (nr, nobs, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), **kw)
+    rng = np.random.default_rng(11)
+    n = 6 if cost == "mmd_opt" else 12
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(4242, 3)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(nobs, 5)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    xo = xo.copy(); xo[0] = np.linspace(2, 60, 100)      # make sure some rollouts actually collide
+    yo = yo.copy(); yo[0] = 1.75
+    got = prob.stage_risk(cost, acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk(cost, acc[i], steer[i], st0, noise_t, xo, yo)
+        _eq(got["risk"][i], ref["risk"], f"risk[{i}]"); _eq(got["lane"][i], ref["lane"], f"lane[{i}]")
+        if cost in ("mmd_opt", "mmd_random"):
+            _eq(got["beta"][i], ref["beta"], "beta"); _eq(got["sigma"][i], ref["sigma"], "sigma")
+        if cost == "mmd_opt":
+            _eq(got["res_beta"][i], ref["res_beta"], "res_beta")
+    assert np.any(got["risk"] != got["risk"][0]) or cost == "saa"
+
+
+def test_stage_select_bit_exact(mods):
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0))
+    rng = np.random.default_rng(13)
+    B = 100
+    for trial in range(4):
+        res = np.abs(rng.normal(0, 1e-5, B)).astype(f32); risk = np.where(rng.random(B) < 0.6, 0.0, rng.random(B)).astype(f32)
+        if trial == 1:
+            res[10:30] = res[10]                 # ties in the first key too
+        base = rng.uniform(5, 50, B).astype(f32)
+        params = np.concatenate([rng.uniform(0.1, 30, (B, 4)), rng.normal(0, 6, (B, 4))], 1).astype(f32)
+        mean = rng.normal(5, 3, 8).astype(f32); A = rng.normal(0, 1, (8, 8)); cov = (A @ A.T + 8 * np.eye(8)).astype(f32)
+        z = rng.normal(0, 1, (95, 8)).astype(f32)
+        g = prob.stage_select("cvar", res, risk, base, params, mean, cov, z)
+        r = ora.select("cvar", res, risk, base, params, mean, cov, z)
+        _eq(g[0], r[0], "params_next"); _eq(g[1], r[1], "mean"); _eq(g[2], r[2], "cov")
+        assert g[3] == r[3]["sel"]
+
+
+def _episodes(O, ora, n, nobs):
+    eps = [O.static_episode(nobs, k) for k in range(n)]
+    tr = [ora.compute_obs_trajectories(*sc) for sc, _ in eps]
+    return [i for _, i in eps], np.stack([t[0] for t in tr]), np.stack([t[1] for t in tr])
+
+
+@pytest.mark.parametrize("cost,noise", [("mmd_opt", "gaussian"), ("cvar", "gaussian"), ("cvar", "beta"), ("mmd_random", "gaussian"), ("saa", "gaussian")])
+def test_solve_small_bit_exact(mods, cost, noise):
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (5, 2, 0.3 if noise == "beta" else 0.1, 30, noise, 0.02, 0.01), **SMALL)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    E = 3
+    idx, xo, yo = _episodes(O, ora, E, 2)
+    got = prob.solve_batch(cost, idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
+    for e in range(E):
+        ref = ora.solve(cost, idx[e], init_state, mean, cov, xo[e], yo[e], v_des)
+        for k in ("cx", "cy", "cost_obs", "cost_lane"):
+            _eq(got[k][e], ref[k], f"{cost}/{noise} ep{e} {k}")
+        if cost == "mmd_opt":
+            for k in ("beta", "sigma", "res_beta"):
+                _eq(got[k][e], ref[k], f"ep{e} {k}")
+
+
+def test_solve_full_size_cvar_matches_oracle(mods):
+    """BASELINE cfg2 shape (static, cvar, beta noise 0.3, 4 obstacles, num_prime 50), full CEM sizes, 6 episodes."""
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (5, 4, 0.3, 50, "beta", 0.0, 0.0), max_episodes=6)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    E = 6
+    idx, xo, yo = _episodes(O, ora, E, 4)
+    got = prob.solve_batch("cvar", idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
+    for e in range(E):
+        ref = ora.solve("cvar", idx[e], init_state, mean, cov, xo[e], yo[e], v_des)
+        for k in ("cx", "cy", "cost_obs", "cost_lane"):
+            _eq(got[k][e], ref[k], f"ep{e} {k}")
+
+
+def test_solve_full_size_mmd_opt_matches_oracle(mods):
+    """BASELINE cfg1: static, mmd_opt, gaussian 0.1, nr 5, 2 obstacles, num_prime 30, full sizes, episode 0 (oracle ~8 s)."""
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), max_episodes=1)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    idx, xo, yo = _episodes(O, ora, 1, 2)
+    got = prob.compute_cem_mmd_opt(idx[0], init_state, mean, cov, xo[0], yo[0], v_des)
+    ref = ora.solve("mmd_opt", idx[0], init_state, mean, cov, xo[0], yo[0], v_des)
+    for g, k in zip(got, ("cx", "cy", "cost_lane", "cost_obs", "beta", "sigma", "res_beta")):
+        _eq(g, ref[k], k)
+
+
+def test_drop_in_module_surface(mods):
+    """`from optimizer import cem` exactly as synthetic_static_obs/main_mpc.py:5-6 does, and the attributes callers read."""
+    import importlib, os, sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mpc-mmd_b200", "synthetic_dynamic_obs")
+    sys.path.insert(1, root)
+    try:
+        sys.modules.pop("optimizer", None); sys.modules.pop("optimizer.cem", None)
+        cem = importlib.import_module("optimizer.cem")
+        prob = cem.CEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0)
+        assert (prob.y_lb, prob.y_ub, prob.cem_helper.K_steer) == (-2.25, -1.25, 0.05)
+        for a in ("nvar", "num_obs", "num", "num_prime", "ker_wt", "P", "Pdot", "Pdot_jax", "Pddot_jax", "t", "wheel_base", "beta_a", "beta_b",
+                  "a_obs", "b_obs", "acc_const_noise", "steer_const_noise"):
+            assert hasattr(prob, a), a
+        x, y, psi = prob.cem_helper.compute_obs_trajectories(np.array([30.0, 40.0]), np.array([1.75, -1.75]), np.array([1.0, 0.0]), np.zeros(2), np.zeros(2))
+        assert x.shape == (2, 100) and abs(x[0, -1] - 45.0) < 1e-4
+    finally:
+        sys.path.remove(root); sys.modules.pop("optimizer", None); sys.modules.pop("optimizer.cem", None)
