@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- MPC solves/sec of the B200 trajectory-optimizer path on BASELINE.json's cfg2 workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the CPU baseline arm (oracle port, all host threads)
+
+One "step" = the 200-episode static sweep of synthetic_static_obs/main_mpc.py:106-128 solved with BOTH cost
+functions of configs[1] (`cvar` and `mmd_opt`; beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5) = 400 solves per GPU.
+Multi-GPU is weak scaling: every rank solves its own 200 episodes (episode ids rank*200 ...), no data-path
+collective; the only exchange is the final NCCL all_gather of the 26-float per-episode record.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "mpc-mmd_b200")):
+    if p not in sys.path:
+        sys.path.insert(1, p)
+
+WORK = dict(num_reduced=5, num_obs=4, noise_level=0.3, num_prime=50, noise="beta", acc_const_noise=0.0, steer_const_noise=0.0)
+COSTS = ("cvar", "mmd_opt")
+EPISODES = 200
+WORKLOAD_NAME = ("configs[1]: synthetic_static_obs, cvar + mmd_opt, beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5, "
+                 "200 episodes per GPU (400 solves/step/GPU)")
+METRIC = "MPC solves/sec"
+
+
+def cem_args():
+    w = WORK
+    return (w["num_reduced"], w["num_obs"], w["noise_level"], w["num_prime"], w["noise"], w["acc_const_noise"], w["steer_const_noise"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself needs jax==0.3.23, absent from this image), naive formulation
+def cpu_arm_step(ora, O, episodes):
+    """solve `episodes` with both costs on the host; returns number of solves"""
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    n = 0
+    for k in episodes:
+        sc, idx = O.static_episode(WORK["num_obs"], k)
+        xo, yo, _ = ora.compute_obs_trajectories(*sc)
+        for cost in COSTS:
+            ora.solve(cost, idx, init_state, mean, cov, xo, yo, v_des)
+            n += 1
+    return n
+
+
+def make_cpu_arm():
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    ora = O.OracleCEM(*cem_args(), variant="static", naive=True)
+    return ora, O, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ora, O, cores = make_cpu_arm()
+    sample = "episode 0 of the sweep, cvar + mmd_opt (2 solves per step), oracle port in the reference's naive formulation, %d host threads" % cores
+    for _ in range(args.warmup):
+        cpu_arm_step(ora, O, [0])
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += cpu_arm_step(ora, O, [0])
+    dt = time.perf_counter() - t0
+    val = n / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample_per_step": "1 episode x 2 costs"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True); self._th.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    import __graft_entry__ as G
+    G.build()
+    from mpcmmd_b200 import CEM, cem_impl, scenes
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, E = max(args.warmup, 3), args.steps, EPISODES
+
+    prob = CEM(*cem_args(), variant="static", max_episodes=E, device=local)
+    eps = list(range(rank * E, rank * E + E))
+    host = scenes.static_batch(prob, eps)
+    keys = ("idx_mpc", "init_state", "mean_param", "cov_param", "x_obs_traj", "y_obs_traj", "v_des")
+    dev_in = {k: torch.as_tensor(host[k], device=dev) for k in keys}
+    pinned = {k: torch.as_tensor(host[k]).pin_memory() for k in keys}
+    pinned_np = {k: pinned[k].numpy() for k in keys}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    thresholds = {"cvar": 1e-5, "mmd_opt": -prob.ker_wt + 1.0}                    # main_mpc.py:88-97
+
+    def record(out, cost):
+        """26-float per-episode record [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] gathered over ranks"""
+        rec = torch.cat([torch.as_tensor(eps, device=dev, dtype=torch.float32)[:, None], (out["cost_obs"] <= thresholds[cost]).float()[:, None],
+                         out["cost_obs"][:, None], out["cost_lane"][:, None], out["cx"], out["cy"]], 1)
+        if world > 1:
+            buf = [torch.empty_like(rec) for _ in range(world)]
+            dist.all_gather(buf, rec)
+            rec = torch.cat(buf, 0)
+        return rec
+
+    def step_device():
+        recs = {}
+        for cost in COSTS:
+            out = prob.solve_batch_device(cost, *[dev_in[k] for k in keys])
+            recs[cost] = record(out, cost)
+        return recs
+
+    def step_host():
+        outs = {}
+        for cost in COSTS:
+            outs[cost] = prob.solve_batch(cost, *[pinned_np[k] for k in keys])
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(W):
+        step_device()
+    launches_per_step = 0
+    for cost in COSTS:            # graphs are cached now; count launches per solve batch
+        prob.solve_batch_device(cost, *[dev_in[k] for k in keys]); launches_per_step += prob.last_launch_count()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)                       # L2 flush between timed steps (outside the event pair)
+            ev[i][0].record()
+            recs = step_device()
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    solves_per_step = E * len(COSTS) * world
+    value = solves_per_step * K / (ms_total * 1e-3)
+    accepted = {c: int(recs[c][:, 1].sum().item()) for c in COSTS}
+
+    # ---- end to end through the host-buffer C ABI call (`e2e`): pinned host inputs, H2D + D2H inside the timed region
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        outs = step_host()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = solves_per_step * K / float(e2e_t.item())
+    h2d = len(COSTS) * sum(int(pinned_np[k].nbytes) for k in keys)
+    d2h = len(COSTS) * sum(int(v.nbytes) for v in outs["mmd_opt"].values())
+    same = all(np.array_equal(outs[c]["cx"], recs[c][rank * E:(rank + 1) * E, 4:15].cpu().numpy()) for c in COSTS)
+
+    # ---- roofline of the dominant kernel (k_risk_opt: rollouts + reduced-set CEM + risk), launch-by-launch CUDA events
+    prob.solve_batch_device("mmd_opt", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+    prof = prob.profile_solve("mmd_opt", E)
+    prof_cvar = None
+    prob.solve_batch_device("cvar", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+    prof_cvar = prob.profile_solve("cvar", E)
+    fl = scenes.flops_per_sample("mmd_opt", WORK["num_reduced"], WORK["num_prime"], WORK["num_obs"])
+    flops_per_launch = fl["risk"] * prob.num_batch * E
+    avg_launch_s = prof["ms"]["risk"] * 1e-3 / prof["launches"]["risk"]
+    peak_tf, sm_count = cem_impl.fp32_peak(local)
+    achieved = flops_per_launch / avg_launch_s / 1e12
+    roofline = {"bound": "fp32", "kernel": "k_risk_opt<5> (rollouts + reduced-set inner CEM + MMD risk)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": "measured in this run: register-resident FP32 fma micro-kernel (MEASURED_PEAKS.json has no FP32 figure)",
+                "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "sm_count": sm_count,
+                "kernel_share_of_mmd_opt_solve": prof["ms"]["risk"] / prof["ms"]["total"],
+                "mmd_opt_ms_by_kernel": prof["ms"], "cvar_ms_by_kernel": prof_cvar["ms"]}
+
+    # ---- per-solve latency at batch = 1 (BASELINE.json's second headline)
+    lat = {}
+    if rank == 0:
+        p1 = CEM(*cem_args(), variant="static", max_episodes=1, device=local)
+        one = {k: dev_in[k][:1].contiguous() for k in keys}
+        for cost in COSTS:
+            for _ in range(5):
+                p1.solve_batch_device(cost, *[one[k] for k in keys])
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(30):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); p1.solve_batch_device(cost, *[one[k] for k in keys]); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            lat[cost] = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95))}
+        del p1
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ora, O, cores = make_cpu_arm()
+        t0 = time.perf_counter()
+        n = cpu_arm_step(ora, O, [0, 1])
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": "episodes 0-1 of the sweep x {cvar, mmd_opt} = 4 solves in %.1f s; oracle port (C, reference's naive formulation), %d host threads" % (dt, cores)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAME, "episodes_per_gpu": E, "costs": list(COSTS), "num_batch": prob.num_batch,
+                           "maxiter_cem": prob.maxiter_cem, "l2": "flushed between timed steps (256 MiB fill)", "parallelism": "episodes sharded %d-way" % world,
+                           "accepted": accepted, "wall_s_timed_region": t_wall},
+                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
+                "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat, "clocks": clk.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -102,6 +102,14 @@ int mpcmmd_solve_host(mpcmmd_handle h, int cost_kind, int n_ep, const int32_t *i
 /* Number of kernel launches the last mpcmmd_solve on this handle issued (graph nodes). */
 int mpcmmd_last_launch_count(mpcmmd_handle h);
 
+/* Measurement aid: re-runs the solve staged by the previous mpcmmd_solve* call launch by launch (no graph) with a
+ * CUDA event after every kernel on the launching stream.  ms[5] = device milliseconds of {setup, projection,
+ * rollout/risk, select, total}; n_launch[4] = launches per class.  Synchronous. */
+int mpcmmd_profile_solve(mpcmmd_handle h, int cost_kind, int n_ep, float *ms, int *n_launch);
+
+/* Measured FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the roofline denominator of the FP32-bound kernels. */
+int mpcmmd_fp32_peak(int device, float *tflops, int *sm_count);
+
 /* ---- stage entry points (teacher-forced parity tests; all DEVICE pointers, synchronous) ---- */
 
 /* deterministic math / RNG primitives: fn 0 exp,1 log,2 log1p,3 sin,4 cos,5 tan,6 atan,7 atan2(y,x),8 erfinv */

@@ -215,30 +215,33 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s) {
 }
 
 // enqueue the whole solve on `s` (captured into a graph by the caller)
-static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s, int* launches) {
+// `marks` (optional, profiling only): an event is recorded after every launch, tagged with its kernel class
+struct LaunchMark { cudaEvent_t ev; int cls; };      // cls: 0 setup (boundary/noise/init), 1 project, 2 risk, 3 select
+static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s, int* launches, std::vector<LaunchMark>* marks = nullptr) {
     const DCfg& d = h->d; DWork& w = h->w;
     const size_t n = (size_t)d.nr * d.np, ncem = (size_t)(d.B - d.n_el) * NPAR;
     int cnt = 0;
-    k_boundary<<<(n_ep + 127) / 128, 128, 0, s>>>(w.init_state, h->beq_x, h->beq_y, h->state0, n_ep); cnt++;
-    k_noise<<<n_ep * d.iters, 128, 0, s>>>(d, w, n_ep, 0, d.iters); cnt++;
-    k_init<<<n_ep, 128, 0, s>>>(d, w, n_ep); cnt++;
+    auto mark = [&](int cls) { cnt++; if (marks) { LaunchMark m; cudaEventCreate(&m.ev); cudaEventRecord(m.ev, s); m.cls = cls; marks->push_back(m); } };
+    k_boundary<<<(n_ep + 127) / 128, 128, 0, s>>>(w.init_state, h->beq_x, h->beq_y, h->state0, n_ep); mark(0);
+    k_noise<<<n_ep * d.iters, 128, 0, s>>>(d, w, n_ep, 0, d.iters); mark(0);
+    k_init<<<n_ep, 128, 0, s>>>(d, w, n_ep); mark(0);
     for (int it = 0; it < d.iters; it++) {
         ProjArgs p = proj_args(h, n_ep);
-        launch_project(h, p, s); cnt++;
+        launch_project(h, p, s); mark(1);
         RiskArgs r;
         r.n_samples = n_ep * d.B; r.B = d.B; r.cost_kind = kind; r.acc = w.acc; r.steer = w.steer; r.state0 = h->state0;
         r.z1 = w.z1 + it * n; r.z2 = w.z2 + it * n; r.z3 = w.z3 + it * n; r.z_stride = (size_t)d.iters * n;
         r.keys = w.keys + it * 4; r.key_stride = (size_t)d.iters * 4;
         r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
         if (launch_risk(h, r, s)) return -1;
-        cnt++;
+        mark(2);
         SelArgs a;
         a.n_ep = n_ep; a.B = d.B; a.it = it; a.nr = d.nr; a.iters_in = d.iters_in; a.w_obs = w_obs_for(h, kind);
         a.res_norm = w.res_norm; a.risk = w.risk; a.lane = w.lane; a.cost_base = w.cost_base; a.params = w.params; a.mean = w.mean; a.cov = w.cov;
         a.zcem = w.zcem + it * ncem; a.z_stride = (size_t)d.iters * ncem; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma;
         a.res_beta = w.res_beta; a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta;
         a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta; a.o_sel = w.o_sel; a.sel_stride = d.iters;
-        k_select<<<n_ep, SEL_THREADS, 2 * d.B * sizeof(float), s>>>(d, a); cnt++;
+        k_select<<<n_ep, SEL_THREADS, 2 * d.B * sizeof(float), s>>>(d, a); mark(3);
     }
     *launches = cnt;
     return 0;
@@ -313,6 +316,32 @@ extern "C" int mpcmmd_solve_host(mpcmmd_handle h, int cost_kind, int n_ep, const
     return 0;
 }
 extern "C" int mpcmmd_last_launch_count(mpcmmd_handle h) { return h ? h->last_launches : 0; }
+
+// Re-run the solve of the inputs staged by the previous mpcmmd_solve* call WITHOUT the graph, with a CUDA event after
+// every launch on the launching stream, and return the device time per kernel class:
+// ms[0] setup (boundary+noise+init), ms[1] projection, ms[2] rollout/risk, ms[3] select, ms[4] total; n_launch[4] likewise.
+extern "C" int mpcmmd_profile_solve(mpcmmd_handle h, int cost_kind, int n_ep, float* ms, int* n_launch) {
+    if (check_solve_args(h, cost_kind, n_ep)) return -1;
+    CK(cudaSetDevice(h->device));
+    std::vector<LaunchMark> marks;
+    cudaEvent_t e0; CK(cudaEventCreate(&e0));
+    cudaStream_t s = h->own_stream;
+    CK(cudaEventRecord(e0, s));
+    int launches = 0;
+    if (enqueue_solve(h, cost_kind, n_ep, s, &launches, &marks)) return -1;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (int i = 0; i < 5; i++) { ms[i] = 0.0f; if (i < 4 && n_launch) n_launch[i] = 0; }
+    cudaEvent_t prev = e0;
+    for (auto& m : marks) {
+        float t = 0.0f; cudaEventElapsedTime(&t, prev, m.ev);
+        ms[m.cls] += t; ms[4] += t; if (n_launch) n_launch[m.cls]++;
+        prev = m.ev;
+    }
+    cudaEventDestroy(e0);
+    for (auto& m : marks) cudaEventDestroy(m.ev);
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // stage entry points (synchronous, default stream)
@@ -401,5 +430,42 @@ extern "C" int mpcmmd_stage_noise(mpcmmd_handle h, int32_t idx_mpc, int32_t iter
     if (z3) CK(cudaMemcpy(z3, w.z3 + slot * n, sizeof(float) * n, cudaMemcpyDeviceToDevice));
     if (z_cem) CK(cudaMemcpy(z_cem, w.zcem + slot * ncem, sizeof(float) * ncem, cudaMemcpyDeviceToDevice));
     if (keys) CK(cudaMemcpy(keys, w.keys + slot * 4, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 FMA peak of this device, measured (the roofline denominator for the FP32-bound kernels; MEASURED_PEAKS.json
+// has only HBM and bf16-GEMM peaks).  8 independent fma chains per thread, 2048 threads per SM resident.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+extern "C" int mpcmmd_fp32_peak(int device, float* tflops, int* sm_count) {
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* buf; CK(cudaMalloc(&buf, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 0.0f;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.0f; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = best;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
     return 0;
 }

@@ -178,6 +178,13 @@ class CEM:
     def last_launch_count(self) -> int:
         return int(self._lib.mpcmmd_last_launch_count(self._h))
 
+    def profile_solve(self, cost, n_ep):
+        """Device time per kernel class of the solve staged by the previous solve call (launch-by-launch CUDA events)."""
+        ms = (C.c_float * 5)(); nl = (C.c_int * 4)()
+        B.check(self._lib.mpcmmd_profile_solve(self._h, B.COST_KINDS[cost], int(n_ep), ms, nl))
+        names = ("setup", "project", "risk", "select")
+        return {"ms": dict(zip(names + ("total",), [float(v) for v in ms])), "launches": dict(zip(names, [int(v) for v in nl]))}
+
     def _single(self, cost, idx_mpc, init_state, mean_param_init, cov_param_init, x_obs_traj, y_obs_traj, v_des):
         r = self.solve_batch(cost, [int(idx_mpc)], np.asarray(init_state, F32)[None], np.asarray(mean_param_init, F32)[None],
                              np.asarray(cov_param_init, F32)[None], np.asarray(x_obs_traj, F32)[None], np.asarray(y_obs_traj, F32)[None],
@@ -295,3 +302,11 @@ def rng_beta(key, a, b, device=0):
     out = torch.empty_like(at)
     B.check(lib.mpcmmd_rng_beta(key[0], key[1], at.data_ptr(), bt.data_ptr(), at.numel(), out.data_ptr(), device))
     return out.cpu().numpy()
+
+
+def fp32_peak(device=0):
+    """(TFLOP/s, SM count): FP32 FMA throughput measured by a register-resident fma micro-kernel."""
+    lib = B.load()
+    tf = C.c_float(); sm = C.c_int()
+    B.check(lib.mpcmmd_fp32_peak(int(device), C.byref(tf), C.byref(sm)))
+    return float(tf.value), int(sm.value)

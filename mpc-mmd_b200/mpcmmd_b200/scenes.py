@@ -1,0 +1,73 @@
+"""Synthetic episode inputs of the reference drivers, restated for the harness / bench:
+obstacle scenes of `compute_obs_data` (synthetic_static_obs/main_mpc.py:10-21), the fixed initial state / CEM mean /
+covariance / v_des (main_mpc.py:46-74; synthetic_dynamic_obs/main_mpc.py:34-62) and the per-episode `idx_mpc`
+draw (`np.random.randint(1,10000)` right after the scene draws, main_mpc.py:113-119)."""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+_X_CHOICES = np.array([35, 40, 45, 50, 55, 60, 65, 70, 75])
+_Y_CHOICES = np.array([-1.75, 1.75])
+
+
+def static_scene(num_obs: int, k: int):
+    """episode k of the static sweep: (x_obs, y_obs, vx_obs, vy_obs, psi_obs), idx_mpc -- legacy NumPy global stream seeded with k"""
+    np.random.seed(k)
+    x = np.random.choice(_X_CHOICES, (num_obs,), replace=False)
+    y = np.random.choice(_Y_CHOICES, (num_obs,))
+    idx_mpc = int(np.random.randint(1, 10000))
+    z = np.zeros(num_obs)
+    return (x, y, z.copy(), z.copy(), z.copy()), idx_mpc
+
+
+def scaled_scene(num_obs: int, k: int):
+    """harness-defined scene for num_obs > 9 (the reference's `choice(..., replace=False)` cannot draw more than 9):
+    x uniform on [15, 75], lane +-1.75, static obstacles, Generator seeded with the episode index."""
+    g = np.random.default_rng(k)
+    x = g.uniform(15.0, 75.0, num_obs)
+    y = g.choice(_Y_CHOICES, num_obs)
+    z = np.zeros(num_obs)
+    return (x, y, z.copy(), z.copy(), z.copy()), int(g.integers(1, 10000))
+
+
+def driver_inputs(variant: str = "static"):
+    y0 = 1.75 if variant == "static" else -1.75
+    init_state = np.array([0.0, y0, 5.0, 0.0, 0.0, 0.0], F32)       # x, y, vx, vy, ax, ay
+    mean = np.array([15.0] * 4 + [0.0] * 4, F32)
+    cov = np.diag(np.array([20.0] * 4 + [100.0] * 4)).astype(F32)
+    return init_state, mean, cov, 15.0
+
+
+def static_batch(prob, episodes, variant="static"):
+    """stacked solve_batch inputs for the given episode indices"""
+    init_state, mean, cov, v_des = driver_inputs(variant)
+    idx, xo, yo = [], [], []
+    for k in episodes:
+        sc, i = static_scene(prob.num_obs, k) if prob.num_obs <= 9 else scaled_scene(prob.num_obs, k)
+        x, y, _ = prob.cem_helper.compute_obs_trajectories(*sc)
+        idx.append(i); xo.append(x); yo.append(y)
+    E = len(idx)
+    return dict(idx_mpc=np.asarray(idx, np.int32), init_state=np.repeat(init_state[None], E, 0), mean_param=np.repeat(mean[None], E, 0),
+                cov_param=np.repeat(cov[None], E, 0), x_obs_traj=np.stack(xo).astype(F32), y_obs_traj=np.stack(yo).astype(F32),
+                v_des=np.full(E, v_des, F32))
+
+
+def flops_per_sample(cost: str, num_reduced: int, num_prime: int, num_obs: int, num_samples_cem=100, maxiter_beta_cem=20):
+    """Algorithmic FLOPs (FMA = 2) of ONE CEM sample in ONE outer iteration, split by kernel -- the minimal formulation of
+    SURVEY.md section 8(d).  Returns dict(project=..., risk=...)."""
+    from math import log2
+    nr, np_, O, S, T, n = num_reduced, num_prime, num_obs, num_samples_cem, 100, 11
+    nm = nr * nr
+    f_guess, f_proj, f_ctrl = 176, 76094, 25 * T
+    opt = cost == "mmd_opt"
+    R = nm if opt else nr
+    f_roll = 30 * R * np_ + 6 * nr * np_
+    f_fit = 2 * nm * (2 * np_ * n + 2 * n * n) if opt else 0
+    f_rs = 0
+    if opt:
+        per_it = S * (2 * nm * log2(nm) + 2 * (nr * nr + nr * nm) + nr * nm + (2.0 / 3.0) * (nr + 1) ** 3 + 2 * (nr + 1) ** 2 + 2 * nr * nr + 2 * nr) \
+            + 2 * S * log2(S) + 11 * (nm + 1) ** 2 + (nm + 1) ** 3 / 3.0 + 89 * (nm + 1) ** 2
+        f_rs = 33 * nm * nm + maxiter_beta_cem * per_it
+    f_cost = 8 * nr * O * np_ + 5 * nr * nr + 3 * nr
+    return dict(project=float(f_guess + f_proj + f_ctrl), risk=float(f_roll + f_fit + f_rs + f_cost))

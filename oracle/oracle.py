@@ -96,6 +96,11 @@ def _fp(a):
     return a.ctypes.data_as(FP)
 
 
+def set_threads(n: int):
+    """host threads oracle_solve splits the B samples of an iteration over (results are independent of n)"""
+    lib().oracle_set_threads(int(n))
+
+
 # ------------------------------------------------------------------------------------------------
 # RNG (JAX 0.3.23 protocol restated in oracle_rng.h)
 

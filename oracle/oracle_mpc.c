@@ -32,6 +32,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include "oracle_math.h"
 #include "oracle_rng.h"
 
@@ -734,6 +735,21 @@ typedef struct {
     float *cxy;        /* (iters, 22) emitted cx,cy */
 } otrace_t;
 
+static int g_oracle_threads = 1;
+void oracle_set_threads(int n) { g_oracle_threads = n; }
+typedef struct {
+    const ocfg_t *c; int cost_kind; const float *params, *beq_x, *beq_y; float v_des; float *lam_x, *lam_y, *s_lane;
+    oproj_out_t *pr; orisk_out_t *rk; const float *st0; const onoise_t *nz; const float *x_obs, *y_obs; int b0, b1;
+} osample_job_t;
+static void *osample_worker(void *arg) {
+    osample_job_t *j = (osample_job_t *)arg;
+    for (int b = j->b0; b < j->b1; b++) {
+        oracle_project(j->c, j->params + b * NP_, j->beq_x, j->beq_y, j->v_des, j->lam_x + b * NV, j->lam_y + b * NV, j->s_lane + b * 2 * NL, &j->pr[b]);
+        oracle_risk(j->c, j->cost_kind, j->pr[b].acc, j->pr[b].steer, j->st0, j->nz, j->x_obs, j->y_obs, &j->rk[b], NULL, NULL);
+    }
+    return NULL;
+}
+
 int oracle_solve(const ocfg_t *c, int cost_kind, int32_t idx_mpc, const float *init_state, const float *mean0,
                  const float *cov0, const float *x_obs, const float *y_obs, float v_des, osolve_out_t *out, otrace_t *tr) {
     int B = c->B, np = c->np, nr = c->nr;
@@ -759,10 +775,18 @@ int oracle_solve(const ocfg_t *c, int cost_kind, int32_t idx_mpc, const float *i
         if (tr && tr->params) memcpy(tr->params + (size_t)it * B * NP_, params, sizeof(float) * B * NP_);
         if (tr && tr->mean) memcpy(tr->mean + it * NP_, mean, sizeof mean);
         if (tr && tr->cov) memcpy(tr->cov + it * NP_ * NP_, cov, sizeof cov);
-        for (int b = 0; b < B; b++) {
-            oracle_project(c, params + b * NP_, beq_x, beq_y, v_des, lam_x + b * NV, lam_y + b * NV, s_lane + b * 2 * NL, &pr[b]);
-            oracle_risk(c, cost_kind, pr[b].acc, pr[b].steer, st0, &nz, x_obs, y_obs, &rk[b], NULL, NULL);
-            res_norm[b] = pr[b].res_norm; risk[b] = rk[b].risk; base[b] = pr[b].cost_base;
+        {   /* the B samples of one iteration are independent: split them over host threads (results do not depend on the split) */
+            int nt = g_oracle_threads < 1 ? 1 : (g_oracle_threads > 256 ? 256 : g_oracle_threads);
+            if (nt > B) nt = B;
+            pthread_t th[256]; osample_job_t jobs[256];
+            for (int k = 0; k < nt; k++) {
+                osample_job_t j = {c, cost_kind, params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane, pr, rk, st0, &nz, x_obs, y_obs,
+                                   (int)((long)B * k / nt), (int)((long)B * (k + 1) / nt)};
+                jobs[k] = j;
+                if (nt > 1) pthread_create(&th[k], NULL, osample_worker, &jobs[k]); else osample_worker(&jobs[k]);
+            }
+            if (nt > 1) for (int k = 0; k < nt; k++) pthread_join(th[k], NULL);
+            for (int b = 0; b < B; b++) { res_norm[b] = pr[b].res_norm; risk[b] = rk[b].risk; base[b] = pr[b].cost_base; }
         }
         oselect_out_t so;
         oracle_select(c, res_norm, risk, base, params, params_next, mean, cov, z_cem, &so);
