@@ -14,7 +14,7 @@ struct Key { uint32_t k0, k1; };
 
 __device__ __forceinline__ uint32_t rotl(uint32_t x, int d) { return (x << d) | (x >> (32 - d)); }
 
-__device__ __forceinline__ void threefry2x32(Key key, uint32_t x0, uint32_t x1, uint32_t& o0, uint32_t& o1) {
+__device__ __noinline__ void threefry2x32(Key key, uint32_t x0, uint32_t x1, uint32_t& o0, uint32_t& o1) {
     const uint32_t ks0 = key.k0, ks1 = key.k1, ks2 = key.k0 ^ key.k1 ^ 0x1BD11BDAu;
     x0 += ks0; x1 += ks1;
 #define TF_R(r) { x0 += x1; x1 = rotl(x1, r); x1 ^= x0; }
@@ -116,7 +116,7 @@ __device__ __forceinline__ float uniform01_from_bits(uint32_t b) {
 __device__ __forceinline__ float normal_elem(Key key, uint32_t n, uint32_t i) { return normal_from_bits(bits_elem(key, n, i)); }
 
 // jax/_src/random.py::_gamma_one(key, alpha, log_space=True): log of a Gamma(alpha,1) sample.
-__device__ float loggamma_one(Key key, float alpha) {
+__device__ __noinline__ float loggamma_one(Key key, float alpha) {
     const float one_over_three = 0.333333343f, squeeze_const = 0.0331f;
     const bool boost_mask = alpha >= 1.0f;
     const float alpha_orig = alpha;
@@ -155,7 +155,7 @@ __device__ float loggamma_one(Key key, float alpha) {
     return (dm::log_(d) + dm::log_(V)) + log_boost;
 }
 // element e (of n) of random.beta(key, a, b, shape) with already-broadcast parameters
-__device__ float beta_elem(Key key, uint32_t n, uint32_t e, float a, float b) {
+__device__ __noinline__ float beta_elem(Key key, uint32_t n, uint32_t e, float a, float b) {
     Key ka, kb; split2(key, ka, kb);
     float lga = loggamma_one(split_row(ka, n, e), a);
     float lgb = loggamma_one(split_row(kb, n, e), b);

@@ -69,6 +69,14 @@ __global__ void k_math_vec(int fn, const float* x, const float* y, float* out, i
         out[i] = v;
     }
 }
+// [iter][row][col] -> [iter][col][row]
+__global__ void k_transpose_tables(const float* src, float* dst, int n_it, int rows, int cols) {
+    const int n = n_it * rows * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int it = i / (rows * cols), rem = i % (rows * cols), r = rem / cols, q = rem % cols;
+        dst[(size_t)it * rows * cols + (size_t)q * rows + r] = src[i];
+    }
+}
 // theta0 = sqrt(20) * z with the bandwidth column clipped (compute_beta.py:41-49, :20-24)
 __global__ void k_theta0(const float* z, int S, int d, float sigma_clip, float* out) {
     const float s20 = sqrtf(20.0f);

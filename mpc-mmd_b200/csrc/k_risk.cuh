@@ -6,9 +6,9 @@
 //   beta_cem.compute_cem (+ compute_mean_cov_beta, compute_beta_reduced)          S/compute_beta.py:93-157, 51-91
 //   kernel_matrix.compute_kernel / compute_mmd (Laplace kernel)                   S/kernel_computation.py:19-87
 //   Costs.compute_f_bar / compute_lane_bar / compute_{mmd,cvar,saa}_{obs,lane}     S/optimizer/costs.py:50-71, 121-234
-// k_risk_base: one warp per sample (cvar / saa / mmd_random: num_reduced rollouts).
-// k_risk_opt : one CTA per sample (mmd_opt: num_reduced^2 mother rollouts + the inner reduced-set CEM,
-//              the dominant cost of a solve), all state in shared memory.
+// k_rollouts : noisy controls + rollouts for a group of samples; finishes cvar / saa / mmd_random.
+// k_inner_cem: one CTA per sample (mmd_opt: the inner reduced-set CEM, the dominant cost of a solve,
+//              plus the MMD risk of the chosen set), all state in shared memory.
 #pragma once
 #include "common.cuh"
 
@@ -25,28 +25,6 @@ struct RiskArgs {
     float *beta, *sigma, *res_beta;  // [n][nr], [n], [n][iters_in]
 };
 
-// perturbed controls (nr,np)  [cem_helper.py:405-443 / 470-508]; threads tid, tid+nt, ...
-__device__ __forceinline__ void noisy_controls(const DCfg& c, const float* acc, const float* steer, const float* z1, const float* z2,
-                                               const float* z3, const uint32_t* keys, float* an, float* sn, int tid, int nt) {
-    const int np = c.np, n = c.nr * np;
-    for (int i = tid; i < n; i += nt) {
-        const int t = i % np;
-        const float a = acc[t], s = steer[t];
-        float pa, ps;
-        if (c.noise_kind == 0) {
-            pa = (c.sigma_acc * fabsf(a)) * z1[i];
-            ps = (c.sigma_steer * fabsf(s)) * z2[i];
-        } else {
-            dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
-            float b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)i, c.beta_a * fabsf(a), c.beta_b * fabsf(a));
-            float b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)i, c.beta_a * fabsf(s), c.beta_b * fabsf(s));
-            pa = c.sigma_acc * (2.0f * b1 - 1.0f);
-            ps = c.ksig_steer * (2.0f * b2 - 1.0f);
-        }
-        an[i] = (a + pa) + c.acc_const * z3[i];
-        sn[i] = (s + ps) + c.steer_const * z3[i];
-    }
-}
 // Euler bicycle rollout, records the state BEFORE each step  [cem_helper.py:380-400, 451-458]
 __device__ __forceinline__ void rollout_one(const DCfg& c, const float* a, const float* s, const float* st0, float* xr, float* yr) {
     float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
@@ -68,7 +46,7 @@ __device__ __forceinline__ float fbar(const DCfg& c, float x, float y, float xo,
     return dm::max0_(cost);
 }
 // Laplace-kernel MMD of nr scalar costs against the zero cost  [kernel_computation.py:67-87]
-__device__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, float sigma) {
+__device__ __noinline__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, float sigma) {
     const int nr = c.nr;
     float s1 = 0.0f, s2 = 0.0f;
     for (int i = 0; i < nr; i++) {
@@ -82,7 +60,7 @@ __device__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, f
     return c.ker_wt * (s1 - 2.0f * s2);
 }
 // jnp.quantile (linear interpolation) + mean of the tail  [costs.py:213-220]
-__device__ float cvar_cost(const DCfg& c, const float* v) {
+__device__ __noinline__ float cvar_cost(const DCfg& c, const float* v) {
     const int nr = c.nr;
     int perm[MPCMMD_MAX_NR_DEV];
     for (int i = 0; i < nr; i++) {            // stable insertion sort, NaN last
@@ -103,118 +81,195 @@ __device__ float cvar_cost(const DCfg& c, const float* v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-#define RISKB_WARPS 4
-__host__ __device__ inline int riskb_warp_floats(int nr, int np) { return 4 * nr * np + 3 * 16; }
+// k_rollouts: noisy controls + Euler rollouts for a group of samples per CTA.  cost kinds with num_reduced rollouts
+// (cvar / saa / mmd_random) finish here with their risk functional; mmd_opt writes the num_reduced^2 mother rollouts and
+// their ridge-fit features for k_inner_cem.  Splitting the solve this way keeps each kernel's instruction footprint
+// inside the 32 KB L1.5 instruction cache (v1 of this file, one fused kernel of 13.7k SASS instructions, spent
+// 6.7 issue slots stalled on instruction fetch per instruction issued -- profiles/r01_v2_summary.md).
+#define ROLL_THREADS 128
+struct RollArgs {
+    RiskArgs r;
+    int spb;                 // samples per CTA
+    int R;                   // rollouts per sample (nr or nr*nr)
+    float *xroll, *yroll;    // [n][R][np]   (mmd_opt only)
+    float* feat;             // [n][nm][22]  (mmd_opt only)
+};
+__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 48); }
 
-__global__ void __launch_bounds__(RISKB_WARPS * 32) k_risk_base(DCfg c, RiskArgs a) {
-    extern __shared__ float sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * RISKB_WARPS + warp;
-    if (g >= a.n_samples) return;
-    const int e = g / a.B, nr = c.nr, np = c.np, n = nr * np;
-    float* an = sm + warp * riskb_warp_floats(nr, np); float* sn = an + n; float* xr = sn + n; float* yr = xr + n;
-    float* cst = yr + n; float* lb = cst + 16; float* ub = lb + 16;
-    noisy_controls(c, a.acc + (size_t)g * T_, a.steer + (size_t)g * T_, a.z1 + e * a.z_stride, a.z2 + e * a.z_stride,
-                   a.z3 + e * a.z_stride, a.keys + e * a.key_stride, an, sn, lane, 32);
-    __syncwarp();
-    for (int r = lane; r < nr; r += 32) rollout_one(c, an + r * np, sn + r * np, a.state0 + e * 5, xr + r * np, yr + r * np);
-    __syncwarp();
-    const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    for (int r = 0; r < nr; r++) {
-        float m = 0.0f, l = 0.0f, u = 0.0f;
-        for (int i = lane; i < c.O * np; i += 32) {
-            const int o = i / np, t = i % np;
-            m = dm::nmax_(m, fbar(c, xr[r * np + t], yr[r * np + t], xo[o * T_ + t], yo[o * T_ + t]));
+__global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
+    extern __shared__ __align__(16) float sm[];
+    const RiskArgs& a = ra.r;
+    const int tid = threadIdx.x, nt = ROLL_THREADS, warp = tid >> 5, lane = tid & 31;
+    const int nr = c.nr, np = c.np, n = nr * np, R = ra.R, spb = ra.spb;
+    const int g0 = blockIdx.x * spb;
+    const int ns = min(spb, a.n_samples - g0);                 // samples in this CTA
+    if (ns <= 0) return;
+    const int per = 2 * n + 2 * R * np + 48;
+    // ---- perturbed controls  [cem_helper.py:405-443 / 470-508]
+#pragma unroll 1
+    for (int i = tid; i < ns * n; i += nt) {
+        const int ls = i / n, el = i % n, t = el % np, g = g0 + ls, e = g / a.B;
+        float* an = sm + ls * per; float* sn = an + n;
+        const float av = a.acc[(size_t)g * T_ + t], sv = a.steer[(size_t)g * T_ + t];
+        const float* z3 = a.z3 + e * a.z_stride;
+        float pa, ps;
+        if (c.noise_kind == 0) {
+            pa = (c.sigma_acc * fabsf(av)) * (a.z1 + e * a.z_stride)[el];
+            ps = (c.sigma_steer * fabsf(sv)) * (a.z2 + e * a.z_stride)[el];
+        } else {
+            const uint32_t* keys = a.keys + e * a.key_stride;
+            dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
+            const float b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+            const float b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+            pa = c.sigma_acc * (2.0f * b1 - 1.0f);
+            ps = c.ksig_steer * (2.0f * b2 - 1.0f);
         }
-        for (int t = lane; t < np; t += 32) {
-            l = dm::nmax_(l, dm::max0_(-yr[r * np + t] + c.y_lb));
-            u = dm::nmax_(u, dm::max0_(yr[r * np + t] - c.y_ub));
-        }
-        m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
-        if (lane == 0) { cst[r] = m; lb[r] = l; ub[r] = u; }
+        an[el] = (av + pa) + c.acc_const * z3[el];
+        sn[el] = (sv + ps) + c.steer_const * z3[el];
     }
-    __syncwarp();
-    if (lane == 0) {
-        float risk, lanec;
-        if (a.cost_kind == 1) {                       // mmd_random: beta = 1/nr, sigma = 0.01, lane = 0  [cem.py:355-356, 404-424]
-            float beta[MPCMMD_MAX_NR_DEV];
-            for (int i = 0; i < nr; i++) { beta[i] = c.beta_del; a.beta[(size_t)g * nr + i] = c.beta_del; }
-            a.sigma[g] = c.sigma_random;
-            risk = mmd_cost(c, beta, cst, c.sigma_random);
-            lanec = 0.0f;
-        } else if (a.cost_kind == 2) {                // cvar  [costs.py:206-221, 137-158]
-            risk = cvar_cost(c, cst);
-            lanec = cvar_cost(c, lb) + cvar_cost(c, ub);
-        } else {                                      // saa  [costs.py:223-234, 160-171]
-            float s = 0.0f, sl = 0.0f, su = 0.0f;
-            for (int i = 0; i < nr; i++) { s = s + (cst[i] > 0.0f ? 1.0f : 0.0f); sl = sl + (lb[i] > 0.0f ? 1.0f : 0.0f); su = su + (ub[i] > 0.0f ? 1.0f : 0.0f); }
-            risk = s / (float)nr;
-            lanec = (sl + su) / (float)nr;
+    __syncthreads();
+    // ---- rollouts: thread (sample, rollout); mmd_opt mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
+    const bool opt = a.cost_kind == 0;
+#pragma unroll 1
+    for (int i = tid; i < ns * R; i += nt) {
+        const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
+        float* an = sm + ls * per; float* sn = an + n; float* xr = sn + n; float* yr = xr + R * np;
+        const int ia = opt ? m / nr : m, is = opt ? m % nr : m;
+        rollout_one(c, an + ia * np, sn + is * np, a.state0 + e * 5, xr + m * np, yr + m * np);
+    }
+    __syncthreads();
+    if (opt) {
+        // ---- mother rollouts + ridge-fit features to global  [cem_helper.py:553-564, folded]
+        const int nm = R;
+#pragma unroll 1
+        for (int i = tid; i < ns * nm * np; i += nt) {
+            const int ls = i / (nm * np), rem = i % (nm * np);
+            const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
+            ra.xroll[(size_t)(g0 + ls) * nm * np + rem] = xr[rem];
+            ra.yroll[(size_t)(g0 + ls) * nm * np + rem] = yr[rem];
         }
-        a.risk[g] = risk; a.lane[g] = lanec;
+#pragma unroll 1
+        for (int i = tid; i < ns * nm * 2 * NV; i += nt) {
+            const int ls = i / (nm * 2 * NV), rem = i % (nm * 2 * NV), m = rem / (2 * NV), k = rem % (2 * NV);
+            const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
+            const float* src = (k < NV) ? xr + m * np : yr + m * np;
+            const float* W = c.Wfit + (k < NV ? k : k - NV) * np;
+            float acc = 0.0f;
+            for (int t = 0; t < np; t++) acc = fmaf(__ldg(W + t), src[t], acc);
+            ra.feat[(size_t)(g0 + ls) * nm * 2 * NV + rem] = acc;
+        }
+        return;
+    }
+    // ---- risk of the nr rollouts (one warp per sample at a time)  [costs.py:50-71, 137-234; cem.py:355-356]
+#pragma unroll 1
+    for (int ls = warp; ls < ns; ls += nt / 32) {
+        const int g = g0 + ls, e = g / a.B;
+        const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
+        float* cst = sm + ls * per + 2 * n + 2 * R * np; float* lb = cst + 16; float* ub = lb + 16;
+        const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
+#pragma unroll 1
+        for (int r = 0; r < nr; r++) {
+            float m = 0.0f, l = 0.0f, u = 0.0f;
+            for (int i = lane; i < c.O * np; i += 32) {
+                const int o = i / np, t = i % np;
+                m = dm::nmax_(m, fbar(c, xr[r * np + t], yr[r * np + t], xo[o * T_ + t], yo[o * T_ + t]));
+            }
+            for (int t = lane; t < np; t += 32) {
+                l = dm::nmax_(l, dm::max0_(-yr[r * np + t] + c.y_lb));
+                u = dm::nmax_(u, dm::max0_(yr[r * np + t] - c.y_ub));
+            }
+            m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
+            if (lane == 0) { cst[r] = m; lb[r] = l; ub[r] = u; }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float risk, lanec;
+            if (a.cost_kind == 1) {                       // mmd_random: beta = 1/nr, sigma = 0.01, lane = 0  [cem.py:355-356, 404-424]
+                float beta[MPCMMD_MAX_NR_DEV];
+                for (int i = 0; i < nr; i++) { beta[i] = c.beta_del; a.beta[(size_t)g * nr + i] = c.beta_del; }
+                a.sigma[g] = c.sigma_random;
+                risk = mmd_cost(c, beta, cst, c.sigma_random);
+                lanec = 0.0f;
+            } else if (a.cost_kind == 2) {                // cvar  [costs.py:206-221, 137-158]
+                risk = cvar_cost(c, cst);
+                lanec = cvar_cost(c, lb) + cvar_cost(c, ub);
+            } else {                                      // saa  [costs.py:223-234, 160-171]
+                float s = 0.0f, sl = 0.0f, su = 0.0f;
+                for (int i = 0; i < nr; i++) { s = s + (cst[i] > 0.0f ? 1.0f : 0.0f); sl = sl + (lb[i] > 0.0f ? 1.0f : 0.0f); su = su + (ub[i] > 0.0f ? 1.0f : 0.0f); }
+                risk = s / (float)nr;
+                lanec = (sl + su) / (float)nr;
+            }
+            a.risk[g] = risk; a.lane[g] = lanec;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// mmd_opt: one CTA per sample
-#define RISKO_THREADS 128
+// k_inner_cem (mmd_opt): one CTA (3 warps) per sample: distance table, the reduced-set CEM, MMD risk of the chosen set.
+// 89 = S - n_elite new beta samples are evaluated per inner iteration (the 11 elites keep last iteration's cost: same
+// row => same arithmetic => same bits), so 96 threads are ~93 % busy in the sample stage and in the row-per-thread
+// resampling stage.
+#define RISKO_THREADS 96
 
-struct OptLayout {          // shared-memory carve-up (in floats)
-    int an, sn, F, D, small, red, uni;   // persistent region offsets; `uni` = start of the aliased region
-    int xr, yr;                          // phase 1 (mother rollouts)
-    int th, thn, cost, betas, idxs, perm, C, rd, mean, xc;   // phase 2 (inner CEM)
-    int xred, yred;                      // phase 3 (rollouts of the chosen reduced set)
-    int total;
+struct OptLayout {          // shared-memory carve-up (in floats); every offset is a multiple of 4 floats (16 B)
+    int F, D, small, red, th, cost, betas, idxs, key64, perm, C, rd, mean, eth, xc, ecost, ebetas, eidxs;
+    int ldc, total;
 };
+__host__ __device__ inline int al4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline OptLayout opt_layout(int nr, int np, int S, int ne) {
     OptLayout L; const int nm = nr * nr, d = nm + 1;
-    int o = 0;
-    L.an = o; o += nr * np; L.sn = o; o += nr * np;
-    L.F = o; o += nm * 2 * NV; L.D = o; o += nm * nm;
-    L.small = o; o += 64;
-    L.red = o; o += 3 * MPCMMD_MAX_NR_DEV * (RISKO_THREADS / 32);
-    L.uni = o;
-    L.xr = o; L.yr = o + nm * np; int p1 = o + 2 * nm * np;
-    int q = o;
-    L.th = q; q += S * d; L.thn = q; q += S * d; L.cost = q; q += S; L.betas = q; q += S * nr; L.idxs = q; q += S * nr;
-    L.perm = q; q += S; L.C = q; q += d * d; L.rd = q; q += d; L.mean = q; q += d; L.xc = q; q += ne * d;
-    L.xred = o; L.yred = o + nr * np; int p3 = o + 2 * nr * np;
-    L.total = p1 > q ? p1 : q; if (p3 > L.total) L.total = p3;
+    (void)np;
+    L.ldc = al4(d);
+    int q = 0;
+    L.F = q; q += al4(nm * 2 * NV); L.D = q; q += al4(nm * nm); L.small = q; q += 64;
+    L.red = q; q += al4(3 * MPCMMD_MAX_NR_DEV * (RISKO_THREADS / 32));
+    L.th = q; q += al4(S * d); L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S * nr);
+    L.key64 = q; q += al4(2 * S); L.perm = q; q += al4(S); L.C = q; q += al4(d * L.ldc); L.rd = q; q += al4(d); L.mean = q; q += al4(d);
+    L.eth = q; q += al4(ne * d); L.xc = q; q += al4(ne * d); L.ecost = q; q += al4(ne); L.ebetas = q; q += al4(ne * nr); L.eidxs = q; q += al4(ne * nr);
+    L.total = q;
     return L;
 }
 
-// one beta sample of the inner CEM: choose the top-NR |theta|, build the Laplace kernels, solve the
-// equality-constrained QP by Cholesky block elimination, return the MMD cost  [compute_beta.py:113-129, 70-91]
+// one beta sample of the inner CEM: choose the top-NR |theta| (stable, ascending), build the Laplace kernels from the
+// chain's distance table, solve the equality-constrained QP by Cholesky block elimination, return the MMD cost
+// [compute_beta.py:113-129, 70-91].  |theta| is compared through its bit pattern (non-negative floats order like
+// integers and NaN patterns sort last), which is the jnp.argsort order.
 template <int NR>
-__device__ __forceinline__ float beta_sample(const DCfg& c, const float* row, const float* D, float* beta_out, int* idx_out) {
-    const int nm = NR * NR;
-    float tv[NR]; int ti[NR];
+__device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
+                                             float* __restrict__ beta_out, int* __restrict__ idx_out) {
+    constexpr int nm = NR * NR;
+    int tv[NR], ti[NR];
 #pragma unroll
-    for (int i = 0; i < NR; i++) { tv[i] = -1.0f; ti[i] = -1; }
-    for (int m = 0; m < nm; m++) {                 // stable "last NR of argsort(|theta|)"
-        const float v = fabsf(row[m]);
-        if (!dm::lt_nanlast(v, tv[0])) {
-            tv[0] = v; ti[0] = m;
-            bool mv = true;
+    for (int i = 0; i < NR; i++) { tv[i] = -1; ti[i] = -1; }
+#pragma unroll 1
+    for (int m = 0; m < nm; m++) {                 // branch-free insertion: replace the smallest, bubble it up past <= elements
+        const int v = (int)(dm::f2u(row[m]) & 0x7fffffffu);
+        bool mv = v >= tv[0];
+        tv[0] = mv ? v : tv[0]; ti[0] = mv ? m : ti[0];
 #pragma unroll
-            for (int p = 0; p < NR - 1; p++) {
-                mv = mv && !dm::lt_nanlast(tv[p], tv[p + 1]);
-                if (mv) { float fv = tv[p]; tv[p] = tv[p + 1]; tv[p + 1] = fv; int iv = ti[p]; ti[p] = ti[p + 1]; ti[p + 1] = iv; }
-            }
+        for (int p = 0; p < NR - 1; p++) {
+            mv = mv && (tv[p] >= tv[p + 1]);
+            const int a0 = tv[p], a1 = tv[p + 1], b0 = ti[p], b1 = ti[p + 1];
+            tv[p] = mv ? a1 : a0; tv[p + 1] = mv ? a0 : a1; ti[p] = mv ? b1 : b0; ti[p + 1] = mv ? b0 : b1;
         }
     }
     const float sigma = row[nm];
     const float rinv = 1.0f / sigma;
     float rowsum[NR];
-    float K[NR][NR];                               // ker_red, full (symmetric bit for bit)
+#pragma unroll
+    for (int i = 0; i < NR; i++) rowsum[i] = 0.0f;
+#pragma unroll 1
+    for (int m = 0; m < nm; m++) {                 // D is symmetric bit for bit: read column m (bank-conflict free across threads)
+        const float* Dm = D + m * nm;
+#pragma unroll
+        for (int i = 0; i < NR; i++) rowsum[i] = rowsum[i] + dm::exp_nonpos(-(Dm[ti[i]] * rinv));
+    }
+    float K[NR][NR];                               // ker_red (symmetric bit for bit); diagonal: exp(-(0 * rinv)) = 1
 #pragma unroll
     for (int i = 0; i < NR; i++) {
-        const float* Di = D + ti[i] * nm;
-        float rs = 0.0f;
-        for (int m = 0; m < nm; m++) rs = rs + dm::exp_nonpos(-(Di[m] * rinv));
-        rowsum[i] = rs;
+        K[i][i] = 1.0f;
 #pragma unroll
-        for (int j = 0; j <= i; j++) { float k = dm::exp_nonpos(-(Di[ti[j]] * rinv)); K[i][j] = k; K[j][i] = k; }
+        for (int j = 0; j < i; j++) { const float k = dm::exp_nonpos(-(D[ti[i] * nm + ti[j]] * rinv)); K[i][j] = k; K[j][i] = k; }
     }
     // A = ker_red + 0.05 I, Cholesky with reciprocal pivots
     float Lm[NR][NR], rd[NR], u[NR], w[NR];
@@ -223,7 +278,7 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* row, co
         float acc = K[j][j] + 0.05f;
 #pragma unroll
         for (int k = 0; k < j; k++) acc = fmaf(-Lm[j][k], Lm[j][k], acc);
-        float dd = sqrtf(acc);
+        const float dd = sqrtf(acc);
         Lm[j][j] = dd; rd[j] = 1.0f / dd;
 #pragma unroll
         for (int i = j + 1; i < NR; i++) {
@@ -268,68 +323,92 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* row, co
     return s1 + s2;
 }
 
+// float -> int64 key whose signed order is "ascending float, -0 == +0, NaN last", tie-broken by the index in the low bits
+__device__ __forceinline__ long long sort_key64(float x, int idx) {
+    const float xz = x + 0.0f;                                   // -0 -> +0
+    const uint32_t ubits = dm::f2u(xz);
+    int k = (ubits & 0x80000000u) ? (int)(~ubits ^ 0x80000000u) : (int)ubits;
+    if (xz != xz) k = 0x7fffffff;
+    return ((long long)k << 12) | (long long)idx;
+}
+
 template <int NR>
-__global__ void __launch_bounds__(RISKO_THREADS) k_risk_opt(DCfg c, RiskArgs a) {
-    extern __shared__ float sm[];
+__global__ void __launch_bounds__(RISKO_THREADS, (NR <= 5) ? 7 : 1) k_inner_cem(DCfg c, RollArgs ra) {
+    extern __shared__ __align__(16) float sm[];
+    const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;
-    const int tid = threadIdx.x, nt = RISKO_THREADS;
-    const int e = g / a.B, np = c.np, nm = NR * NR, d = nm + 1, S = c.S_in, ne = c.n_el_in;
+    constexpr int nm = NR * NR, d = nm + 1;
+    constexpr bool SMALL = d <= 32;
+    const int tid = threadIdx.x, nt = RISKO_THREADS, warp = tid >> 5, lane = tid & 31;
+    const int e = g / a.B, np = c.np, S = c.S_in, ne = c.n_el_in;
     const OptLayout L = opt_layout(NR, np, S, ne);
-    float* an = sm + L.an; float* sn = sm + L.sn; float* F = sm + L.F; float* D = sm + L.D; float* small = sm + L.small;
-    float* xr = sm + L.xr; float* yr = sm + L.yr;
-    // ---- phase 1: controls, mother rollouts, features, distance table
-    noisy_controls(c, a.acc + (size_t)g * T_, a.steer + (size_t)g * T_, a.z1 + e * a.z_stride, a.z2 + e * a.z_stride,
-                   a.z3 + e * a.z_stride, a.keys + e * a.key_stride, an, sn, tid, nt);
-    __syncthreads();
-    const float* st0 = a.state0 + e * 5;
-    for (int m = tid; m < nm; m += nt)             // mother sample m = i*nr + j: acc noise i, steer noise j  [cem_helper.py:510-511]
-        rollout_one(c, an + (m / NR) * np, sn + (m % NR) * np, st0, xr + m * np, yr + m * np);
-    __syncthreads();
-    for (int i = tid; i < nm * 2 * NV; i += nt) {  // ridge-fit features  [cem_helper.py:553-564, folded]
-        const int m = i / (2 * NV), k = i % (2 * NV);
-        const float* src = (k < NV) ? xr + m * np : yr + m * np;
-        const float* W = c.Wfit + (k < NV ? k : k - NV) * np;
-        float acc = 0.0f;
-        for (int t = 0; t < np; t++) acc = fmaf(W[t], src[t], acc);
-        F[i] = acc;
+    const int ldc = L.ldc;
+    float* F = sm + L.F; float* D = sm + L.D; float* small = sm + L.small;
+    // ---- distance table of the mother features  [kernel_computation.py:31-33]
+    {
+        const float* Fg = ra.feat + (size_t)g * nm * 2 * NV;
+#pragma unroll 1
+        for (int i = tid; i < nm * 2 * NV; i += nt) F[i] = Fg[i];
     }
     __syncthreads();
-    for (int i = tid; i < nm * nm; i += nt) {      // L1 distances between mother features  [kernel_computation.py:31-33]
+#pragma unroll 1
+    for (int i = tid; i < nm * nm; i += nt) {
         const float* Fa = F + (i / nm) * 2 * NV; const float* Fb = F + (i % nm) * 2 * NV;
         float dist = 0.0f;
 #pragma unroll
         for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
         D[i] = dist;
     }
-    __syncthreads();                               // xr / yr are dead from here on (aliased by the CEM state)
-    // ---- phase 2: inner CEM  [compute_beta.py:93-157]
-    float* th = sm + L.th; float* thn = sm + L.thn; float* cost = sm + L.cost; float* betas = sm + L.betas;
-    int* idxs = (int*)(sm + L.idxs); int* perm = (int*)(sm + L.perm);
-    float* C = sm + L.C; float* rd = sm + L.rd; float* mean = sm + L.mean; float* xc = sm + L.xc;
-    for (int i = tid; i < S * d; i += nt) th[i] = c.theta0[i];
+    // ---- inner CEM  [compute_beta.py:93-157]
+    float* th = sm + L.th; float* cost = sm + L.cost; float* betas = sm + L.betas; int* idxs = (int*)(sm + L.idxs);
+    long long* key64 = (long long*)(sm + L.key64); int* perm = (int*)(sm + L.perm);
+    float* C = sm + L.C; float* mean = sm + L.mean; float* eth = sm + L.eth; float* xc = sm + L.xc;
+    float* ecost = sm + L.ecost; float* ebetas = sm + L.ebetas; int* eidxs = (int*)(sm + L.eidxs);
+#pragma unroll 1
+    for (int i = tid; i < S * d; i += nt) th[i] = __ldg(c.theta0 + i);
     __syncthreads();
     float* resb = a.res_beta + (size_t)g * c.iters_in;
+#pragma unroll 1
     for (int it = 0; it < c.iters_in; it++) {
-        for (int s = tid; s < S; s += nt) cost[s] = beta_sample<NR>(c, th + s * d, D, betas + s * NR, idxs + s * NR);
+        // -- evaluate the new samples (all of them in iteration 0; afterwards rows 0..ne-1 are last iteration's elites)
+#pragma unroll 1
+        for (int s = (it == 0 ? 0 : ne) + tid; s < S; s += nt) cost[s] = beta_sample<NR>(c, th + s * d, D, betas + s * NR, idxs + s * NR);
         __syncthreads();
-        for (int s = tid; s < S; s += nt) {        // stable argsort by rank counting (NaN last)
-            const float v = cost[s];
+#pragma unroll 1
+        for (int s = tid; s < S; s += nt) key64[s] = sort_key64(cost[s], s);
+        __syncthreads();
+#pragma unroll 1
+        for (int s = tid; s < S; s += nt) {        // stable argsort by rank counting; only the ne best are needed
+            const long long ks = key64[s];
             int rank = 0;
-            for (int j = 0; j < S; j++) { const float u = cost[j]; rank += (dm::lt_nanlast(u, v) || (!dm::lt_nanlast(v, u) && j < s)) ? 1 : 0; }
-            perm[rank] = s;
+#pragma unroll 4
+            for (int j = 0; j < S; j++) rank += (key64[j] < ks) ? 1 : 0;
+            if (rank < ne) perm[rank] = s;
         }
         __syncthreads();
-        for (int i = tid; i < ne * d; i += nt) thn[i] = th[perm[i / d] * d + (i % d)];      // elites keep their rank order
-        __syncthreads();
-        for (int i = tid; i < d; i += nt) {        // mean over the elites  [compute_beta.py:60]
+        // -- gather the elites (rank order) and their mean  [compute_beta.py:56-60]
+#pragma unroll 1
+        for (int i = tid; i < ne * d; i += nt) eth[i] = th[perm[i / d] * d + (i % d)];
+#pragma unroll 1
+        for (int i = tid; i < ne * NR; i += nt) { const int src = perm[i / NR] * NR + (i % NR); ebetas[i] = betas[src]; eidxs[i] = idxs[src]; }
+#pragma unroll 1
+        for (int i = tid; i < ne; i += nt) ecost[i] = cost[perm[i]];
+#pragma unroll 1
+        for (int i = tid; i < d; i += nt) {
             float s = 0.0f;
-            for (int el = 0; el < ne; el++) s = s + thn[el * d + i];
+            for (int el = 0; el < ne; el++) s = s + th[perm[el] * d + i];
             mean[i] = s / (float)ne;
         }
         __syncthreads();
-        for (int i = tid; i < ne * d; i += nt) xc[i] = thn[i] - mean[i % d];
+#pragma unroll 1
+        for (int i = tid; i < ne * d; i += nt) { const float v = eth[i]; th[i] = v; xc[i] = v - mean[i % d]; }
+#pragma unroll 1
+        for (int i = tid; i < ne * NR; i += nt) { betas[i] = ebetas[i]; idxs[i] = eidxs[i]; }
+#pragma unroll 1
+        for (int i = tid; i < ne; i += nt) cost[i] = ecost[i];
         __syncthreads();
+#pragma unroll 1
         for (int i = tid; i < d * d; i += nt) {    // jnp.cov (ddof = 1) + 0.05 I, lower triangle  [compute_beta.py:61]
             const int r = i / d, q = i % d;
             if (q <= r) {
@@ -337,70 +416,115 @@ __global__ void __launch_bounds__(RISKO_THREADS) k_risk_opt(DCfg c, RiskArgs a) 
                 for (int el = 0; el < ne; el++) acc = fmaf(xc[el * d + r], xc[el * d + q], acc);
                 acc = acc / (float)(ne - 1);
                 if (r == q) acc = acc + 0.05f;
-                C[i] = acc;
+                C[r * ldc + q] = acc;
             }
         }
         __syncthreads();
-        for (int j = 0; j < d; j++) {              // Cholesky, column by column (rows in parallel); contract order: ascending-k fma chain
-            for (int r = j + tid; r < d; r += nt) {
-                float acc = C[r * d + j];
-                for (int k = 0; k < j; k++) acc = fmaf(-C[r * d + k], C[j * d + k], acc);
-                if (r == j) { const float dd = sqrtf(acc); C[j * d + j] = dd; rd[j] = 1.0f / dd; }
-                else C[r * d + j] = acc;                        // provisional, scaled by 1/L[j][j] after the barrier
+        if constexpr (SMALL) {
+            // -- Cholesky by warp 0, one row per lane, left-looking: acc = a_ij - sum_k<j L_ik L_jk as an ascending-k fma chain
+            if (warp == 0) {
+#pragma unroll 1
+                for (int j = 0; j < d; j++) {
+                    float acc = 0.0f;
+                    if (lane >= j && lane < d) {
+                        acc = C[lane * ldc + j];
+                        for (int k = 0; k < j; k++) acc = fmaf(-C[lane * ldc + k], C[j * ldc + k], acc);
+                    }
+                    const float ajj = __shfl_sync(FULL, acc, j);
+                    const float dd = sqrtf(ajj);
+                    const float rdj = 1.0f / dd;
+                    if (lane == j) C[j * ldc + j] = dd;
+                    else if (lane > j && lane < d) C[lane * ldc + j] = acc * rdj;
+                    __syncwarp();
+                }
             }
             __syncthreads();
-            for (int r = j + 1 + tid; r < d; r += nt) C[r * d + j] = C[r * d + j] * rd[j];
-            __syncthreads();
+            // -- resample: one thread per new row, normals in registers, L broadcast from shared memory  [compute_beta.py:63-66]
+            const int nrow = S - ne;
+            const float* zT = c.zb_iterT + (size_t)it * d * nrow;
+#pragma unroll 1
+            for (int r = tid; r < nrow; r += nt) {
+                float z[d];
+#pragma unroll
+                for (int k = 0; k < d; k++) z[k] = __ldg(zT + k * nrow + r);
+                float* dst = th + (ne + r) * d;
+#pragma unroll
+                for (int q = 0; q < d; q++) {
+                    const float4* Cq = reinterpret_cast<const float4*>(C + q * ldc);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int k4 = 0; k4 <= q / 4; k4++) {
+                        const float4 l = Cq[k4];
+                        if (4 * k4 + 0 <= q) acc = fmaf(l.x, z[4 * k4 + 0], acc);
+                        if (4 * k4 + 1 <= q) acc = fmaf(l.y, z[4 * k4 + 1], acc);
+                        if (4 * k4 + 2 <= q) acc = fmaf(l.z, z[4 * k4 + 2], acc);
+                        if (4 * k4 + 3 <= q) acc = fmaf(l.w, z[4 * k4 + 3], acc);
+                    }
+                    float v = mean[q] + acc;
+                    if (q == nm) v = (v != v) ? v : (v > c.sigma_clip ? v : c.sigma_clip);
+                    dst[q] = v;
+                }
+            }
+        } else {
+            float* rd = sm + L.rd;
+#pragma unroll 1
+            for (int j = 0; j < d; j++) {          // block-wide Cholesky, column by column; contract order: ascending-k fma chain
+                for (int r = j + tid; r < d; r += nt) {
+                    float acc = C[r * ldc + j];
+                    for (int k = 0; k < j; k++) acc = fmaf(-C[r * ldc + k], C[j * ldc + k], acc);
+                    if (r == j) { const float dd = sqrtf(acc); C[j * ldc + j] = dd; rd[j] = 1.0f / dd; }
+                    else C[r * ldc + j] = acc;                  // provisional, scaled by 1/L[j][j] after the barrier
+                }
+                __syncthreads();
+                for (int r = j + 1 + tid; r < d; r += nt) C[r * ldc + j] = C[r * ldc + j] * rd[j];
+                __syncthreads();
+            }
+            const float* z = c.zb_iter + (size_t)it * (S - ne) * d;
+#pragma unroll 1
+            for (int i = tid; i < (S - ne) * d; i += nt) {
+                const int r = i / d, q = i % d;
+                float v = mvn_elem(C, ldc, q, z + r * d, mean[q]);
+                if (q == nm) v = (v != v) ? v : (v > c.sigma_clip ? v : c.sigma_clip);
+                th[(ne + r) * d + q] = v;
+            }
         }
-        const float* z = c.zb_iter + (size_t)it * (S - ne) * d;
-        for (int i = tid; i < (S - ne) * d; i += nt) {         // resample  [compute_beta.py:63-64]
-            const int r = i / d, q = i % d;
-            thn[(ne + r) * d + q] = mvn_elem(C, d, q, z + r * d, mean[q]);
-        }
-        __syncthreads();
-        for (int s = tid; s < S; s += nt) { float v = thn[s * d + nm]; thn[s * d + nm] = (v != v) ? v : (v > c.sigma_clip ? v : c.sigma_clip); }
         __syncthreads();
         if (tid == 0) {
-            const int imin = perm[0];
-            resb[it] = cost[imin];
+            resb[it] = ecost[0];
             if (it == c.iters_in - 1) {            // beta / reduced set of the best sample; sigma from the RESAMPLED array [Q7]
-                for (int i = 0; i < NR; i++) { small[i] = betas[imin * NR + i]; ((int*)small)[16 + i] = idxs[imin * NR + i]; }
-                small[48] = thn[imin * d + nm];
+                for (int i = 0; i < NR; i++) { small[i] = ebetas[i]; ((int*)small)[16 + i] = eidxs[i]; }
+                small[48] = th[perm[0] * d + nm];
             }
         }
         __syncthreads();
-        float* tmp = th; th = thn; thn = tmp;
     }
-    // ---- phase 3: risk of the chosen reduced set  [costs.py:173-186, 121-135]
-    float* xred = sm + L.xred; float* yred = sm + L.yred;
+    // ---- risk of the chosen reduced set (its rollouts come back from global memory)  [costs.py:173-186, 121-135]
     const int* ridx = (const int*)small + 16;
-    for (int i = tid; i < NR; i += nt) {
-        const int m = ridx[i];
-        rollout_one(c, an + (m / NR) * np, sn + (m % NR) * np, st0, xred + i * np, yred + i * np);
-    }
-    __syncthreads();
+    const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
     const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    const int warp = tid >> 5, lane = tid & 31;
-    float* red = sm + L.red;  // per-warp partial maxima, 3 * NR * (threads/32) floats
+    constexpr int NW = RISKO_THREADS / 32;
+    float* red = sm + L.red;  // per-warp partial maxima, 3 * NR * NW floats
+#pragma unroll 1
     for (int r = 0; r < NR; r++) {
+        const float* xred = xg + ridx[r] * np; const float* yred = yg + ridx[r] * np;
         float m = 0.0f, l = 0.0f, u = 0.0f;
         for (int i = tid; i < c.O * np; i += nt) {
             const int o = i / np, t = i % np;
-            m = dm::nmax_(m, fbar(c, xred[r * np + t], yred[r * np + t], xo[o * T_ + t], yo[o * T_ + t]));
+            m = dm::nmax_(m, fbar(c, xred[t], yred[t], xo[o * T_ + t], yo[o * T_ + t]));
         }
         for (int t = tid; t < np; t += nt) {
-            l = dm::nmax_(l, dm::max0_(-yred[r * np + t] + c.y_lb));
-            u = dm::nmax_(u, dm::max0_(yred[r * np + t] - c.y_ub));
+            l = dm::nmax_(l, dm::max0_(-yred[t] + c.y_lb));
+            u = dm::nmax_(u, dm::max0_(yred[t] - c.y_ub));
         }
         m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
-        if (lane == 0) { red[(r * 3 + 0) * 4 + warp] = m; red[(r * 3 + 1) * 4 + warp] = l; red[(r * 3 + 2) * 4 + warp] = u; }
+        if (lane == 0) { red[(r * 3 + 0) * NW + warp] = m; red[(r * 3 + 1) * NW + warp] = l; red[(r * 3 + 2) * NW + warp] = u; }
     }
     __syncthreads();
     if (tid == 0) {
         float cs[NR], lbv[NR], ubv[NR], beta[NR];
         for (int r = 0; r < NR; r++) {
-            float m = red[(r * 3 + 0) * 4], l = red[(r * 3 + 1) * 4], u = red[(r * 3 + 2) * 4];
-            for (int wv = 1; wv < RISKO_THREADS / 32; wv++) { m = dm::nmax_(m, red[(r * 3 + 0) * 4 + wv]); l = dm::nmax_(l, red[(r * 3 + 1) * 4 + wv]); u = dm::nmax_(u, red[(r * 3 + 2) * 4 + wv]); }
+            float m = red[(r * 3 + 0) * NW], l = red[(r * 3 + 1) * NW], u = red[(r * 3 + 2) * NW];
+            for (int wv = 1; wv < NW; wv++) { m = dm::nmax_(m, red[(r * 3 + 0) * NW + wv]); l = dm::nmax_(l, red[(r * 3 + 1) * NW + wv]); u = dm::nmax_(u, red[(r * 3 + 2) * NW + wv]); }
             cs[r] = m; lbv[r] = l; ubv[r] = u; beta[r] = small[r];
             a.beta[(size_t)g * NR + r] = small[r];
         }

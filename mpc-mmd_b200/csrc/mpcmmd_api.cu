@@ -1,5 +1,5 @@
 // mpcmmd_api.cu -- C ABI of libmpcmmd.so (see include/mpcmmd.h): handle lifetime, the batched
-// solve (one CUDA graph of 2 + 3*maxiter_cem kernels per (cost kind, episode count)) and the
+// solve (one CUDA graph of 3 + (3 or 4)*maxiter_cem kernels per (cost kind, episode count)) and the
 // stage entry points used by the teacher-forced parity tests.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -26,6 +26,7 @@ struct mpcmmd_handle_s {
     DCfg d;
     DWork w;
     float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
+    float *xroll = nullptr, *yroll = nullptr, *feat = nullptr;     // mmd_opt scratch (ensure_opt_scratch)
     int E = 0;
     std::vector<void*> allocs;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
@@ -62,19 +63,32 @@ __global__ void k_boundary(const float* init_state, float* beq_x, float* beq_y, 
     state0[e * 5 + 4] = dm::atan2_(s[3], s[2]);
 }
 
-static size_t risk_opt_smem(const DCfg& d) { return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float); }
-static size_t risk_base_smem(const DCfg& d) { return (size_t)RISKB_WARPS * riskb_warp_floats(d.nr, d.np) * sizeof(float); }
+static size_t inner_cem_smem(const DCfg& d) { return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float); }
+// samples per CTA of k_rollouts: as many as keep one thread per rollout busy (bounded by shared memory), but never so
+// many that a small batch leaves SMs idle (latency at batch = 1 episode)
+static int roll_spb(const DCfg& d, int kind, int n_samples) {
+    const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
+    int spb = ROLL_THREADS / R; if (spb < 1) spb = 1; if (spb > 8) spb = 8;
+    while (spb > 1 && (size_t)roll_smem_floats(spb, d.nr, d.np, R) * sizeof(float) > 96 * 1024) spb--;
+    while (spb > 1 && (n_samples + spb - 1) / spb < 4 * 148) spb--;
+    return spb;
+}
+static size_t roll_smem_for(const DCfg& d, int kind, int spb) {
+    const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
+    return (size_t)roll_smem_floats(spb, d.nr, d.np, R) * sizeof(float);
+}
+static size_t roll_smem(const DCfg& d, int kind) { return roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30)); }
 
-typedef void (*risk_opt_fn)(DCfg, RiskArgs);
-static risk_opt_fn pick_risk_opt(int nr) {
+typedef void (*inner_cem_fn)(DCfg, RollArgs);
+static inner_cem_fn pick_inner_cem(int nr) {
     switch (nr) {
-        case 2: return k_risk_opt<2>;
-        case 3: return k_risk_opt<3>;
-        case 4: return k_risk_opt<4>;
-        case 5: return k_risk_opt<5>;
-        case 6: return k_risk_opt<6>;
-        case 8: return k_risk_opt<8>;
-        case 10: return k_risk_opt<10>;
+        case 2: return k_inner_cem<2>;
+        case 3: return k_inner_cem<3>;
+        case 4: return k_inner_cem<4>;
+        case 5: return k_inner_cem<5>;
+        case 6: return k_inner_cem<6>;
+        case 8: return k_inner_cem<8>;
+        case 10: return k_inner_cem<10>;
         default: return nullptr;
     }
 }
@@ -161,15 +175,22 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
             split0(dk);                                                           // compute_beta.py:54
             k_normal_table<<<64, 256>>>(dk[0], dk[1], (S - ne) * dd, zb + (size_t)it * (S - ne) * dd);
         }
-        d.z_init = z_init; d.theta0 = theta0; d.zb_iter = zb;
+        float* zbT;
+        if (dalloc(h, &zbT, (size_t)d.iters_in * (S - ne) * dd)) { mpcmmd_destroy(h); return -1; }
+        k_transpose_tables<<<64, 256>>>(zb, zbT, d.iters_in, S - ne, dd);
+        d.z_init = z_init; d.theta0 = theta0; d.zb_iter = zb; d.zb_iterT = zbT;
     }
     // opt-in shared memory sizes
     if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
-    if (risk_base_smem(d) > 48 * 1024 && cudaFuncSetAttribute(k_risk_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)risk_base_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_risk_base smem opt-in failed"); }
-    risk_opt_fn f = pick_risk_opt(nr);
+    {
+        size_t rs = roll_smem(d, MPCMMD_COST_MMD_OPT); const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
+        if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
+        if (rs > 48 * 1024 && cudaFuncSetAttribute(k_rollouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
+    }
+    inner_cem_fn f = pick_inner_cem(nr);
     if (f) {
-        if (risk_opt_smem(d) > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)risk_opt_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_risk_opt smem opt-in failed"); }
+        if (inner_cem_smem(d) > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inner_cem_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CK(cudaDeviceSynchronize());
@@ -202,14 +223,31 @@ static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s)
     k_project<<<blocks, PROJ_WARPS * 32, PROJ_SMEM_BYTES, s>>>(h->d, p);
     return 0;
 }
-static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s) {
-    if (r.cost_kind == MPCMMD_COST_MMD_OPT) {
-        risk_opt_fn f = pick_risk_opt(h->d.nr);
+// mother rollouts / features scratch of the mmd_opt path, allocated on first use ([E*B][nm][np] x2 and [E*B][nm][22])
+static int ensure_opt_scratch(mpcmmd_handle_s* h) {
+    if (h->xroll) return 0;
+    const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
+    if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
+    return 0;
+}
+// rollouts (+ risk for the num_reduced-rollout costs); mmd_opt continues with the inner CEM kernel.  Returns launches issued.
+static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, int* n_launch = nullptr) {
+    const DCfg& d = h->d;
+    const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
+    if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
+    RollArgs ra;
+    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat;
+    inner_cem_fn f = nullptr;
+    if (opt) {
+        f = pick_inner_cem(d.nr);
         if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
-        f<<<r.n_samples, RISKO_THREADS, risk_opt_smem(h->d), s>>>(h->d, r);
-    } else {
-        const int blocks = (r.n_samples + RISKB_WARPS - 1) / RISKB_WARPS;
-        k_risk_base<<<blocks, RISKB_WARPS * 32, risk_base_smem(h->d), s>>>(h->d, r);
+        if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
+    }
+    k_rollouts<<<(r.n_samples + ra.spb - 1) / ra.spb, ROLL_THREADS, roll_smem_for(d, r.cost_kind, ra.spb), s>>>(d, ra);
+    if (n_launch) *n_launch = 1;
+    if (opt) {
+        f<<<r.n_samples, RISKO_THREADS, inner_cem_smem(d), s>>>(d, ra);
+        if (n_launch) *n_launch = 2;
     }
     return 0;
 }
@@ -233,8 +271,9 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         r.z1 = w.z1 + it * n; r.z2 = w.z2 + it * n; r.z3 = w.z3 + it * n; r.z_stride = (size_t)d.iters * n;
         r.keys = w.keys + it * 4; r.key_stride = (size_t)d.iters * 4;
         r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
-        if (launch_risk(h, r, s)) return -1;
-        mark(2);
+        int nl = 0;
+        if (launch_risk(h, r, s, &nl)) return -1;
+        mark(2); if (nl == 2) cnt++;
         SelArgs a;
         a.n_ep = n_ep; a.B = d.B; a.it = it; a.nr = d.nr; a.iters_in = d.iters_in; a.w_obs = w_obs_for(h, kind);
         a.res_norm = w.res_norm; a.risk = w.risk; a.lane = w.lane; a.cost_base = w.cost_base; a.params = w.params; a.mean = w.mean; a.cov = w.cov;
@@ -250,7 +289,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
 static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
     auto key = std::make_pair(kind, n_ep);
     auto it = h->graphs.find(key);
-    if (it != h->graphs.end()) { *out = it->second; h->last_launches = 3 + 3 * h->d.iters; return 0; }
+    if (it != h->graphs.end()) { *out = it->second; h->last_launches = 3 + (kind == MPCMMD_COST_MMD_OPT ? 4 : 3) * h->d.iters; return 0; }
     cudaGraph_t g;
     int launches = 0;
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
@@ -282,6 +321,7 @@ static int solve_impl(mpcmmd_handle_s* h, int kind, int n_ep, const int32_t* idx
     if (!idx_mpc || !init_state || !mean || !cov || !x_obs || !y_obs || !v_des || !out) return fail("mpcmmd_solve: null pointer");
     CK(cudaSetDevice(h->device));
     const DCfg& d = h->d; DWork& w = h->w;
+    if (kind == MPCMMD_COST_MMD_OPT && ensure_opt_scratch(h)) return -1;
     cudaGraphExec_t ge;
     if (get_graph(h, kind, n_ep, &ge)) return -1;
     CK(cudaMemcpyAsync(w.idx_mpc, idx_mpc, sizeof(int32_t) * n_ep, in_kind, s));
@@ -395,6 +435,7 @@ extern "C" int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const fl
     RiskArgs r;
     r.n_samples = n; r.B = n; r.cost_kind = cost_kind; r.acc = acc; r.steer = steer; r.state0 = state0; r.z1 = z1; r.z2 = z2; r.z3 = z3; r.z_stride = 0;
     r.keys = keys; r.key_stride = 0; r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
+    if (cost_kind == MPCMMD_COST_MMD_OPT && ensure_opt_scratch(h)) return -1;
     if (launch_risk(h, r, 0)) return -1;
     CK(cudaDeviceSynchronize());
     return 0;

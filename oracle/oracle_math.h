@@ -20,10 +20,10 @@
 static inline uint32_t om_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float om_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-/* exp(x): x clamped to [-87, 88] (below -87 the result is flushed to 0). */
+/* exp(x): x clamped to [-87, 88] (so exp(x < -87) = exp(-87) ~ 1.6e-38, exp(x > 88) = exp(88)). */
 static inline float om_exp(float x) {
     if (x != x) return x;
-    if (x < -87.0f) return 0.0f;
+    if (x < -87.0f) x = -87.0f;
     if (x > 88.0f) x = 88.0f;
     const float MAGIC = 12582912.0f; /* 1.5 * 2^23: adding it rounds to nearest integer */
     float t = fmaf(x, 1.44269504088896341f, MAGIC);
