@@ -7,7 +7,7 @@
  * algorithm per function, built only from IEEE-754 round-to-nearest +,-,*,/,sqrt,fma and integer
  * bit operations, so that a second implementation (the CUDA kernels) can reproduce every bit.
  * The algorithms are the classic Cody-Waite / minimax single-precision forms (Cephes family);
- * tests/test_oracle_math.py bounds their error against glibc (<= 2 ulp on the ranges used).
+ * tests/test_cpu_oracle.py bounds their error against glibc (<= 3 ulp; 4 ulp for sin/cos of |x| up to 100).
  *
  * Compile with -ffp-contract=off: every fused multiply-add below is an explicit fmaf().
  */

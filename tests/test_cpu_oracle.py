@@ -1,0 +1,291 @@
+"""CPU suite (-m "not gpu"): pins the oracle against every external known answer available for this path and checks the
+host-side logic and the C ABI surface.  No GPU compute happens here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+f32 = np.float32
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle as O
+    return O
+
+
+# ---- RNG known answers -------------------------------------------------------------------------------
+def test_threefry_random123_kat(O):
+    assert O.threefry(0x13198a2e, 0x03707344, 0x243f6a88, 0x85a308d3) == (0xc4923a9c, 0x483df7a0)
+
+
+def test_split_prngkey0_matches_jax_docs(O):
+    assert O.split((0, 0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert O.split0((0, 0)) == (4146024105, 967050713)
+
+
+def test_normal_prngkey0_matches_jax_docs(O):
+    assert abs(float(O.normal((0, 0), 1)[0]) - (-0.20584226)) < 2e-7
+
+
+def test_bits_layout_odd_even(O):
+    # bits(key, n): first half / second half of the counters are the two Threefry words; odd n pads with a literal 0
+    k = (123, 456)
+    b5, b6 = O.bits(k, 5), O.bits(k, 6)
+    a0, _ = O.threefry(*k, 0, 3); assert b5[0] == a0 == b6[0]
+    a2, b2 = O.threefry(*k, 2, 0); assert b5[2] == a2            # padded counter
+    _, c2 = O.threefry(*k, 2, 5); assert b6[5] == c2
+
+
+def test_normal_moments_and_uniform_range(O):
+    z = O.normal((7, 11), 200000)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and np.isfinite(z).all()
+    u = O.uniform((7, 11), 100000)
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+
+
+def test_beta_sampler_moments(O):
+    a = np.full(20000, 2.0 * 1.3, f32); b = np.full(20000, 5.0 * 1.3, f32)       # beta_a*|u|, beta_b*|u| with |u| = 1.3
+    s = O.beta((3, 4), a, b)
+    assert np.all((s > 0) & (s < 1))
+    assert abs(s.mean() - 2.0 / 7.0) < 0.01
+    assert abs(s.var() - (2.6 * 6.5) / ((9.1 ** 2) * 10.1)) < 0.003
+    lo = O.beta((3, 4), np.full(4000, 0.2, f32), np.full(4000, 0.5, f32))       # alpha < 1: log-space boost path
+    assert abs(lo.mean() - 2.0 / 7.0) < 0.03
+
+
+# ---- deterministic math against glibc ----------------------------------------------------------------------------------
+def _ulps(got, ref64):
+    ref = ref64.astype(f32)
+    spacing = np.abs(np.nextafter(ref, f32(np.inf)) - ref).astype(np.float64)
+    spacing[spacing == 0] = 1e-45
+    return np.abs(got.astype(np.float64) - ref64) / spacing
+
+
+@pytest.mark.parametrize("fn,lo,hi,ref,tol", [("exp", -87.0, 88.0, np.exp, 1.0), ("log", 1e-30, 1e6, np.log, 1.0), ("log1p", -0.9999, 5.0, np.log1p, 2.5),
+                                              ("sin", -100.0, 100.0, np.sin, 4.0), ("cos", -100.0, 100.0, np.cos, 4.0), ("sin", -7.0, 7.0, np.sin, 2.0), ("cos", -7.0, 7.0, np.cos, 2.0), ("tan", -1.5, 1.5, np.tan, 3.0),
+                                              ("atan", -100.0, 100.0, np.arctan, 3.0)])
+def test_oracle_math_accuracy(O, fn, lo, hi, ref, tol):
+    x = np.random.default_rng(0).uniform(lo, hi, 300000).astype(f32)
+    assert _ulps(O.math_vec(fn, x), ref(x.astype(np.float64))).max() <= tol
+
+
+def test_oracle_math_special_values(O):
+    assert O.math_vec("exp", np.array([-1000.0], f32))[0] == O.math_vec("exp", np.array([-87.0], f32))[0] > 0      # clamp, part of the contract
+    assert np.isneginf(O.math_vec("log", np.array([0.0], f32))[0]) and np.isnan(O.math_vec("log", np.array([-1.0], f32))[0])
+    x = np.array([0.0, -1.0, 1.0, 0.0], f32); y = np.array([0.0, 0.0, 0.0, 1.0], f32)
+    np.testing.assert_allclose(O.math_vec("atan2", x, y), [0.0, np.pi, 0.0, np.pi / 2], atol=1e-7)
+    a = np.random.default_rng(1).normal(0, 3, (2, 100000)).astype(f32)
+    assert _ulps(O.math_vec("atan2", a[0], a[1]), np.arctan2(a[1].astype(np.float64), a[0].astype(np.float64))).max() <= 3.5
+
+
+# ---- golden vectors from the reference's own Bernstein file ------------------------------------------------------------
+def test_bernstein_matches_reference_golden(O, built):
+    g = np.load(os.path.join(GOLD, "bernstein_ref.npz"))
+    from mpcmmd_b200 import constants as K
+    tot_time = np.linspace(0, 15, 100)
+    for impl in (lambda: O.bernstein_basis(tot_time[0], tot_time[-1], tot_time), lambda: K.bernstein_coeff_order10_new(10, tot_time[0], tot_time[-1], tot_time)):
+        P, Pd, Pdd = impl()
+        for got, name in ((P, "P"), (Pd, "Pdot"), (Pdd, "Pddot")):
+            np.testing.assert_allclose(got, g[name], rtol=1e-12, atol=1e-13)
+            a32, r32 = got.astype(f32), g[name].astype(f32)                             # the float32 cast the solver uses (cem.py:48)
+            diff = a32 != r32
+            if name != "Pddot":
+                assert not diff.any(), name
+            else:   # 4 of 1100 entries (t = 1/3, 2/3) are zeros of the second derivative: both sides hold ~1e-17 cancellation residue
+                assert diff.sum() <= 4 and np.all(np.abs(a32[diff]) < 1e-15) and np.all(np.abs(r32[diff]) < 1e-15)
+
+
+@pytest.mark.parametrize("npr", [20, 30, 50, 60, 100])
+def test_p_prime_float32_close_to_reference_float64(O, built, npr):
+    from mpcmmd_b200 import constants as K
+    g = np.load(os.path.join(GOLD, "bernstein_ref.npz"))[f"P_prime_{npr}"]
+    a, b = O.bernstein_P_f32(npr, npr * 0.15), K.bernstein_P_prime_f32(npr, npr * 0.15)
+    assert a.dtype == f32 and np.array_equal(a, b)
+    np.testing.assert_allclose(a, g, atol=2e-6)
+    np.testing.assert_allclose(a.sum(1), 1.0, atol=1e-5)                               # partition of unity
+
+
+def test_product_constants_equal_oracle_constants(O, built):
+    from mpcmmd_b200 import constants as K
+    for npr in (30, 50):
+        hc = K.build_constants(npr); ora = O.OracleCEM(5, 2, 0.1, npr, "gaussian", 0.0, 0.0)
+        for a, b in ((hc.P, ora.P), (hc.Pdot, ora.Pd), (hc.Pddot, ora.Pdd), (hc.Gx, ora.Gx), (hc.Gy, ora.Gy), (hc.Kx, ora.Kx), (hc.Ky, ora.Ky), (hc.Wfit, ora.Wfit)):
+            assert a.dtype == f32 and np.array_equal(a, b)
+
+
+def test_folded_solves_equal_literal_solves(O):
+    """D2: the folded constant inverses reproduce the literal KKT solves of cem_helper.py:216-223 / projection.py:145-168."""
+    ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0)
+    P, Pd, Pdd = (a.astype(np.float64) for a in (ora.P, ora.Pd, ora.Pdd))
+    rng = np.random.default_rng(0)
+    v = rng.uniform(1, 25, 4); y = rng.normal(0, 3, 4); bx = np.array([0.0, 5.0, 0.2]); by = np.array([1.75, 0.1, -0.1, 0.0])
+    A_eq_x = np.vstack((P[0], Pd[0], Pdd[0])); A_eq_y = np.vstack((P[0], Pd[0], Pdd[0], Pd[-1]))
+    Qx = 100 * Pdd.T @ Pdd; Qy = Qx.copy(); lx = np.zeros(11); ly = np.zeros(11)
+    for q in range(4):
+        s = slice(25 * q, 25 * q + 25)
+        Avd, Apd = Pdd[s] - 2 * Pd[s], Pdd[s] - 2 * P[s]
+        Qx += Avd.T @ Avd; Qy += Apd.T @ Apd
+        lx += -Avd.T @ (-2 * v[q] * np.ones(25)); ly += -Apd.T @ (-2 * y[q] * np.ones(25))
+    sx = np.linalg.solve(np.block([[Qx, A_eq_x.T], [A_eq_x, np.zeros((3, 3))]]), np.concatenate((-lx, bx)))[:11]
+    sy = np.linalg.solve(np.block([[Qy, A_eq_y.T], [A_eq_y, np.zeros((4, 4))]]), np.concatenate((-ly, by)))[:11]
+    np.testing.assert_allclose(ora.Gx.astype(np.float64) @ np.concatenate((v, bx)), sx, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(ora.Gy.astype(np.float64) @ np.concatenate((y, by)), sy, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(A_eq_x @ sx, bx, atol=1e-8)
+
+
+# ---- properties of the stages --------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["static", "dynamic"])
+def test_projection_properties(O, variant):
+    ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0, variant=variant)
+    rng = np.random.default_rng(3)
+    bx = np.array([0.0, 5.0, 0.0], f32); by = np.array([1.75 if variant == "static" else -1.75, 0.0, 0.0, 0.0], f32)
+    P, Pd, Pdd = (a.astype(np.float64) for a in (ora.P, ora.Pd, ora.Pdd))
+    for _ in range(10):
+        p = np.concatenate([rng.uniform(2, 25, 4), rng.normal(0, 4, 4)]).astype(f32)
+        lx, ly, sl = np.zeros(11, f32), np.zeros(11, f32), np.zeros(198, f32)
+        o = ora.project(p, bx, by, 15.0, lx, ly, sl)
+        cx, cy = o["cx"].astype(np.float64), o["cy"].astype(np.float64)
+        np.testing.assert_allclose([P[0] @ cx, Pd[0] @ cx, Pdd[0] @ cx], bx, atol=2e-3)           # A_eq_x c = b_eq_x   (projection.py:154-171)
+        np.testing.assert_allclose([P[0] @ cy, Pd[0] @ cy, Pdd[0] @ cy, Pd[-1] @ cy], by, atol=2e-3)
+        assert (sl >= 0).all() and np.isfinite(o["res_norm"]) and o["res_norm"] >= 0                  # s_lane >= 0       (projection.py:182)
+        assert o["acc"][99] == 0.0                                                                     # Q10
+        assert o["cost_base"] >= o["res_norm"]
+
+
+def test_mmd_floor_and_cvar_rule(O):
+    ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0)
+    init_state, mean, cov, v_des = O.driver_inputs()
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    far_x = np.full((2, 100), 500.0, f32); far_y = np.full((2, 100), 1.75, f32)
+    acc = np.zeros(100, f32); steer = np.zeros(100, f32)
+    nz = ora.noise_tables(17, 0)
+    r = ora.risk("mmd_random", acc, steer, st0, nz, far_x, far_y)
+    assert abs(float(r["risk"]) + 1000.0) < 1e-2 and np.all(r["red_cost"] == 0)                        # Q12: all costs 0 -> -ker_wt
+    r = ora.risk("cvar", acc, steer, st0, nz, far_x, far_y)
+    assert float(r["risk"]) == 0.0
+    near_x = np.tile(np.linspace(0, 75, 100, dtype=f32), (2, 1))                                      # obstacle riding along with the ego car
+    r = ora.risk("cvar", acc, steer, st0, nz, near_x, far_y, want_rollouts=True)
+    assert float(r["risk"]) == r["red_cost"].max() > 0.9                                               # Q19: nr = 5, alpha = .98 -> CVaR = max cost
+    r = ora.risk("saa", acc, steer, st0, nz, near_x, far_y)
+    assert float(r["risk"]) == 1.0
+
+
+def test_inner_cem_beta_sums_to_one_and_cost_decreases(O):
+    ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    rng = np.random.default_rng(5)
+    acc = rng.normal(0, 1.0, 100).astype(f32); steer = rng.normal(0, 0.02, 100).astype(f32)
+    xo = np.full((2, 100), 40.0, f32); yo = np.full((2, 100), 1.75, f32)
+    r = ora.risk("mmd_opt", acc, steer, st0, ora.noise_tables(99, 1), xo, yo)
+    assert abs(r["beta"].sum() - 1.0) < 1e-4                                                           # equality constraint of the beta QP (compute_beta.py:35-36,79)
+    assert r["sigma"] >= 0.01 and len(set(r["red_idx"].tolist())) == 5 and r["red_idx"].max() < 25
+    assert r["res_beta"][-1] <= r["res_beta"][0] + 1e-6                                                # elitist CEM: best cost never increases
+    assert np.all(np.diff(r["res_beta"]) <= 1e-6)
+    assert float(r["risk"]) >= -1000.0 - 1e-2                                                          # mmd >= -ker_wt (kernel_computation.py:82-87)
+
+
+def test_naive_and_table_formulations_are_bit_identical(O):
+    kw = dict(num_batch=20, maxiter_cem=2, num_samples_cem=30, maxiter_beta_cem=3)
+    init_state, mean, cov, v_des = O.driver_inputs()
+    sc, idx = O.static_episode(2, 1)
+    outs = []
+    for naive in (False, True):
+        ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0, naive=naive, **kw)
+        xo, yo, _ = ora.compute_obs_trajectories(*sc)
+        outs.append(ora.solve("mmd_opt", idx, init_state, mean, cov, xo, yo, v_des))
+    for k in ("cx", "cy", "cost_obs", "beta", "sigma", "res_beta"):
+        assert np.array_equal(outs[0][k], outs[1][k])
+
+
+def test_threaded_oracle_is_deterministic(O):
+    kw = dict(num_batch=20, maxiter_cem=2)
+    ora = O.OracleCEM(5, 4, 0.3, 50, "beta", 0.0, 0.0, **kw)
+    init_state, mean, cov, v_des = O.driver_inputs()
+    sc, idx = O.static_episode(4, 2); xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    O.set_threads(1); a = ora.solve("cvar", idx, init_state, mean, cov, xo, yo, v_des)
+    O.set_threads(5); b = ora.solve("cvar", idx, init_state, mean, cov, xo, yo, v_des)
+    O.set_threads(1)
+    assert np.array_equal(a["cx"], b["cx"]) and np.array_equal(a["cy"], b["cy"]) and a["cost_obs"] == b["cost_obs"]
+
+
+def test_oracle_regression_pins(O):
+    """the oracle's own outputs are frozen (tests/golden/oracle_solves.npz, made by make_golden.py) so that contract changes are deliberate"""
+    pins = np.load(os.path.join(GOLD, "oracle_solves.npz"))
+    small = dict(num_batch=24, maxiter_cem=3, num_samples_cem=40, maxiter_beta_cem=4)
+    for name, args, cost, variant in (("mmd_opt_g", (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), "mmd_opt", "static"), ("cvar_b", (5, 4, 0.3, 50, "beta", 0.0, 0.0), "cvar", "static"),
+                                      ("saa_g_dyn", (4, 3, 0.1, 20, "gaussian", 0.02, 0.01), "saa", "dynamic"), ("mmd_random_g", (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), "mmd_random", "static")):
+        ora = O.OracleCEM(*args, variant=variant, **small)
+        st, mn, cv, vd = O.driver_inputs(variant)
+        sc, idx = O.static_episode(args[1], 3); xo, yo, _ = ora.compute_obs_trajectories(*sc)
+        r = ora.solve(cost, idx, st, mn, cv, xo, yo, vd)
+        for k in ("cx", "cy", "cost_obs", "cost_lane", "beta", "sigma"):
+            assert np.array_equal(np.asarray(r[k]), pins[f"{name}.{k}"], equal_nan=True), (name, k)
+
+
+def test_solve_semantics_quirks(O):
+    """Q1/Q2: the emitted row is row 0 of the 20 risk-sorted samples of the LAST iteration."""
+    ora = O.OracleCEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0, num_batch=40, maxiter_cem=4)
+    init_state, mean, cov, v_des = O.driver_inputs()
+    sc, idx = O.static_episode(2, 0); xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    r = ora.solve("cvar", idx, init_state, mean, cov, xo, yo, v_des, trace=True)
+    tr = r["trace"]
+    res, risk = tr["res_norm"][-1], tr["risk"][-1]
+    order = sorted(range(40), key=lambda i: (risk[i], res[i], i))
+    assert r["sel"] == order[0] == tr["sel"][-1]
+    assert np.array_equal(r["cx"], tr["cxy"][-1][:11]) and r["cost_obs"] == risk[order[0]]
+    assert np.array_equal(tr["params"][1][:5, 0] >= 0.1, np.ones(5, bool))                             # next batch starts with the 5 elites
+    assert idx == 6745                                                                                 # S/main_mpc.py episode 0, num_obs 2
+
+
+# ---- C ABI surface -------------------------------------------------------------------------------------------------------
+def test_abi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "mpcmmd.h")).read()
+    declared = set(re.findall(r"\b(mpcmmd_[a-z0-9_]+)\s*\(", hdr))
+    from mpcmmd_b200 import binding
+    lib = ctypes.CDLL(binding.LIB_PATH)
+    assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mpcmmd_version() == 100
+    assert ctypes.sizeof(binding.MpcmmdConfig) == 12 * 4 + 27 * 4 + 4 + 8 * 8          # ints, floats, padding, pointers
+
+
+def test_product_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mpcmmd_b200 import CEM, binding
+    with pytest.raises(binding.MpcmmdError):
+        CEM(5, 2, 0.1, 30, "gaussian", 0.0, 0.0)
+    cfg = binding.MpcmmdConfig(); h = ctypes.c_void_p()
+    lib = binding.load()
+    assert lib.mpcmmd_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0 and b"CUDA" in lib.mpcmmd_last_error()
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for base in ("mpc-mmd_b200",):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle", txt, re.M):
+                        bad.append(f)
+    assert not bad, bad
+
+
+def test_scene_generators_match(O, built):
+    from mpcmmd_b200 import scenes
+    for nobs in (2, 4, 6):
+        for k in (0, 1, 7, 199, 250):
+            (a, ia), (b, ib) = O.static_episode(nobs, k), scenes.static_scene(nobs, k)
+            assert ia == ib and all(np.array_equal(x, y) for x, y in zip(a, b))
+    fl = scenes.flops_per_sample("mmd_opt", 5, 30, 2)
+    assert abs(20 * 100 * (fl["project"] + fl["risk"]) / 7.07e9 - 1.0) < 0.02          # cfg1 mmd_opt = 7.07 GFLOP per solve
