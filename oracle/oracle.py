@@ -5,8 +5,9 @@ Python face of the plain-C oracle (oracle_mpc.c): builds the constants of ``CEM.
 reference's scene generators (S/main_mpc.py:10-21, D/obs_data_generate_dynamic.py) so tests and
 bench.py's ``cpu_baseline`` leg can run the same episodes as the CUDA path.
 
-PARITY UNPINNED (see oracle_mpc.c header): only the RNG known answers and the Bernstein basis
-(tests/golden/bernstein_*.npz, generated from the reference's own file) are pinned externally.
+Parity pins (see oracle_mpc.c header / DESIGN.md section 4): RNG known answers, the reference's own Bernstein file, and
+tests/golden/ref_stages.npz (stage vectors recorded from the reference's own optimizer source running on a NumPy
+stand-in for JAX).  jax.random.beta's rejection sampler is the one piece that remains restated-but-unpinned.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """
 from __future__ import annotations

