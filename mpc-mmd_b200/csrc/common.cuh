@@ -39,6 +39,7 @@ struct DWork {
     float *z1, *z2, *z3;           // [E][iters][nr*np]
     float *zcem;                   // [E][iters][(B-n_el)*8]
     uint32_t *keys;                // [E][iters][4]
+    float *btab;                   // [E][iters][4][GT_FIELDS][nr*np]  Beta-sampler candidate table (beta noise only)
     // staged inputs
     int32_t *idx_mpc;              // [E]
     float *init_state;             // [E][6]

@@ -165,4 +165,83 @@ __device__ __noinline__ float beta_elem(Key key, uint32_t n, uint32_t e, float a
     return ga / (ga + gb);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Replay form of the Beta sampler.  Every random number _gamma_one consumes is a pure function of (element key, round r,
+// inner try j) -- the Gamma parameter only decides which of them are accepted -- and the reference gives all num_batch
+// samples of an episode the SAME key (cem_helper.py:109-110, in_axes=(0,0,None,None)).  So the candidates are drawn once per
+// (episode, iteration, element) into a table (gamma_table_fill, ~30 Threefry calls) and each of the 100 samples replays the
+// acceptance test on them (loggamma_replay: 2 logs, no Threefry).  The table holds rounds 0..2 (and a second inner try for
+// round 0); a sample that needs more (probability ~5e-4) falls back to loggamma_one.  Bit-identical to beta_elem.
+#define GT_FIELDS 11   // x00, x01, U0, logU0, x10, U1, logU1, x20, U2, logU2, log1p(-u_boost)
+
+// stream: 0/1 = (ka, kb) of the acceleration key, 2/3 = (ka, kb) of the steering key
+__device__ __forceinline__ Key gamma_stream_key(Key k_acc, Key k_steer, int stream) {
+    Key ka, kb; split2(stream < 2 ? k_acc : k_steer, ka, kb);
+    return (stream & 1) ? kb : ka;
+}
+__device__ __forceinline__ void gamma_table_fill(Key stream_key, uint32_t n, uint32_t e, float* t /* field f at t[f*n] */) {
+    Key key = split_row(stream_key, n, e);
+    Key subkey;
+    { Key k0; split2(key, k0, subkey); key = k0; }
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+        Key xk, uk;
+        { Key k0; split3(key, k0, xk, uk); key = k0; }
+        Key s0, s1; split2(xk, s0, s1);
+        const int base = r == 0 ? 0 : (r == 1 ? 4 : 7);
+        t[(size_t)base * n] = normal_from_bits(bits1(s1));
+        int fu = base + 1;
+        if (r == 0) { Key s0b, s1b; split2(s0, s0b, s1b); t[(size_t)1 * n] = normal_from_bits(bits1(s1b)); fu = 2; }
+        const float U = uniform01_from_bits(bits1(uk));
+        t[(size_t)fu * n] = U; t[(size_t)(fu + 1) * n] = dm::log_(U);
+    }
+    const float u = uniform01_from_bits(bits1(subkey));
+    t[(size_t)10 * n] = dm::log1p_(-u);
+}
+__device__ __forceinline__ float loggamma_replay(const float* __restrict__ t, size_t n, float alpha, bool& ok) {
+    const float one_over_three = 0.333333343f, squeeze_const = 0.0331f;
+    const bool boost_mask = alpha >= 1.0f;
+    const float alpha_orig = alpha;
+    alpha = boost_mask ? alpha : alpha + 1.0f;
+    const float d = alpha - one_over_three;
+    const float c = one_over_three / sqrtf(d);
+    float x = t[0];
+    float v = 1.0f + x * c;
+    if (v <= 0.0f) { x = t[n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false; }
+    float X = x * x, V = (v * v) * v, lv = dm::log_(V);
+    bool cont;
+    { const float U = t[2 * n], LU = t[3 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+    if (cont) {
+        x = t[4 * n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false;
+        X = x * x; V = (v * v) * v; lv = dm::log_(V);
+        { const float U = t[5 * n], LU = t[6 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+        if (cont) {
+            x = t[7 * n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false;
+            X = x * x; V = (v * v) * v; lv = dm::log_(V);
+            { const float U = t[8 * n], LU = t[9 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+            if (cont) ok = false;
+        }
+    }
+    const float lb = t[10 * n];
+    float log_boost;
+    if (boost_mask || lb == 0.0f) log_boost = 0.0f;
+    else log_boost = lb * (1.0f / alpha_orig);
+    return (dm::log_(d) + lv) + log_boost;
+}
+// element e of random.beta(key, a, b): tab -> [2 streams (a, b)][GT_FIELDS][n]; (ka, kb) = split(key) for the fallback
+__device__ __forceinline__ float beta_replay(const float* __restrict__ tab, Key key, uint32_t n, uint32_t e, float a, float b) {
+    bool oka = true, okb = true;
+    float lga = loggamma_replay(tab + e, n, a, oka);
+    float lgb = loggamma_replay(tab + (size_t)GT_FIELDS * n + e, n, b, okb);
+    if (!(oka && okb)) {                       // rare: more candidates needed than the table holds
+        Key ka, kb; split2(key, ka, kb);
+        if (!oka) lga = loggamma_one(split_row(ka, n, e), a);
+        if (!okb) lgb = loggamma_one(split_row(kb, n, e), b);
+    }
+    float m = lga > lgb ? lga : lgb;
+    if (lga != lga || lgb != lgb) m = DM_NAN;
+    float ga = dm::exp_(lga - m), gb = dm::exp_(lgb - m);
+    return ga / (ga + gb);
+}
+
 }  // namespace dr

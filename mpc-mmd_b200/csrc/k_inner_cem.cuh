@@ -1,0 +1,528 @@
+// k_inner_cem.cuh -- the reduced-set inner CEM of mmd_opt for num_reduced^2 + 1 <= 32 (num_reduced <= 5), the dominant
+// kernel of a solve.  Same arithmetic contract as k_inner_cem_gen (k_risk.cuh) and oracle_inner_cem (bit for bit), but
+// mapped for instruction issue, which is what bounds it (profiles/r01_v3_summary.md):
+//   * Laplace-kernel exponentials two at a time on Blackwell's packed FP32 pipe (FFMA2 / FADD2 / FMUL2, IEEE per lane),
+//   * top-num_reduced |theta| selection on packed (value | index) integer keys with min/max (exact path on near ties),
+//   * elite selection by ONE warp with redux.sync min over per-lane sorted candidate lists (no O(S^2) rank count),
+//   * covariance, Cholesky (row per lane, right-looking, in registers) and the multivariate-normal resampling in
+//     packed FP32 with float4 shared-memory operands.
+// Replaces beta_cem.compute_cem (S/compute_beta.py:93-157) + kernel_matrix.compute_kernel (S/kernel_computation.py:19-65)
+// + Costs.compute_mmd_obs / compute_mmd_lane (S/optimizer/costs.py:121-135, 173-186).
+#pragma once
+#include "k_risk.cuh"
+
+namespace pk {   // packed float32x2 arithmetic (sm_100a): each lane is an IEEE-754 round-to-nearest operation
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 dup(float v) { return pack(v, v); }
+__device__ __forceinline__ void unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo(f2 v) { float a, b; unpack(v, a, b); return a; }
+__device__ __forceinline__ float hi(f2 v) { float a, b; unpack(v, a, b); return b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// two dm::exp_nonpos at once (same operations in the same order per lane; the 2^n scaling is a float multiply so NaN survives)
+__device__ __forceinline__ f2 exp2_nonpos(float xa, float xb) {
+    const float MAGIC = 12582912.0f;
+    float sa, sb;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(sa) : "f"(xa), "f"(-87.0f));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(sb) : "f"(xb), "f"(-87.0f));
+    const f2 xs = pack(sa, sb);
+    const f2 t = fma2(xs, dup(1.44269504088896341f), dup(MAGIC));
+    const f2 nf = add2(t, dup(-MAGIC));
+    f2 r = fma2(nf, dup(-0.693359375f), xs);
+    r = fma2(nf, dup(2.12194440e-4f), r);
+    f2 p = dup(1.9875691500e-4f);
+    p = fma2(p, r, dup(1.3981999507e-3f));
+    p = fma2(p, r, dup(8.3334519073e-3f));
+    p = fma2(p, r, dup(4.1665795894e-2f));
+    p = fma2(p, r, dup(1.6666665459e-1f));
+    p = fma2(p, r, dup(5.0000001201e-1f));
+    const f2 z = mul2(r, r);
+    const f2 y = add2(fma2(p, z, r), dup(1.0f));
+    float ta, tb; unpack(t, ta, tb);
+    // bits(t) = bits(MAGIC) + n and bits(MAGIC) << 23 == 0 (mod 2^32)  =>  (bits(t) << 23) + 0x3f800000 = bits(2^n)
+    const float sca = dm::u2f((dm::f2u(ta) << 23) + 0x3f800000u), scb = dm::u2f((dm::f2u(tb) << 23) + 0x3f800000u);
+    return mul2(y, pack(sca, scb));
+}
+}  // namespace pk
+
+#define ICF_THREADS 96
+#define ICF_MAX_S 128       // candidates per inner iteration handled by the one-warp selection (4 per lane)
+#define ICF_MAX_NE 12       // elites (covariance operands are read as 3 float4 per column)
+
+struct FastLayout {         // shared-memory carve-up in floats; every offset is a multiple of 4 floats
+    int D, th, cost, betas, idxs, eth, ecost, ebetas, eidxs, perm, xc, C, mean, small, red, total;
+    int ldt, ldc;
+};
+__host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
+    FastLayout L; const int nm = nr * nr, d = nm + 1;
+    L.ldt = d | 1;                           // odd row stride: thread-per-row accesses are bank-conflict free
+    L.ldc = al4(d);
+    int q = 0;
+    L.D = q; q += al4(nm * nm);
+    L.th = q; q += al4(S * L.ldt > nm * 2 * NV ? S * L.ldt : nm * 2 * NV);      // new rows; aliased by the mother features while D is built
+    L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S);      // idxs: num_reduced 5-bit indices packed per row
+    L.eth = q; q += 2 * al4(ne * L.ldt); L.ecost = q; q += 2 * al4(ne); L.ebetas = q; q += 2 * al4(ne * nr); L.eidxs = q; q += 2 * al4(ne);
+    L.perm = q; q += al4(ne);
+    L.xc = q; q += ICF_MAX_NE * L.ldc;       // centered elites, row el, 16-byte aligned rows
+    L.C = q; q += d * L.ldc;                 // covariance (lower, row-major); overwritten in place by L transposed (LT[k][q] = L[q][k])
+    L.mean = q; q += L.ldc;
+    L.small = q; q += 64; L.red = q; q += al4(3 * nr * (ICF_THREADS / 32));
+    L.total = q;
+    return L;
+}
+
+// exact top-NR |theta| (stable, ascending) -- used when the packed keys below cannot decide
+template <int NR>
+__device__ __noinline__ int top_abs_exact(const float* __restrict__ row) {     // returns the indices packed 5 bits each
+    constexpr int nm = NR * NR;
+    int tv[NR], ti[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) { tv[i] = -1; ti[i] = -1; }
+#pragma unroll 1
+    for (int m = 0; m < nm; m++) {
+        const int v = (int)(dm::f2u(row[m]) & 0x7fffffffu);
+        bool mv = v >= tv[0];
+        tv[0] = mv ? v : tv[0]; ti[0] = mv ? m : ti[0];
+#pragma unroll
+        for (int p = 0; p < NR - 1; p++) {
+            mv = mv && (tv[p] >= tv[p + 1]);
+            const int a0 = tv[p], a1 = tv[p + 1], b0 = ti[p], b1 = ti[p + 1];
+            tv[p] = mv ? a1 : a0; tv[p + 1] = mv ? a0 : a1; ti[p] = mv ? b1 : b0; ti[p + 1] = mv ? b0 : b1;
+        }
+    }
+    int packed = 0;
+#pragma unroll
+    for (int i = 0; i < NR; i++) packed |= ti[i] << (5 * i);
+    return packed;
+}
+
+// one beta sample of the inner CEM [compute_beta.py:113-129, 70-91]; bit-identical to beta_sample<NR> of k_risk.cuh
+template <int NR>
+__device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
+                                                  float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
+    constexpr int nm = NR * NR;
+    static_assert(nm <= 32, "index must fit in the 5 low key bits");
+    // ---- top-NR |theta|: keys (|theta| bits with the 5 low bits replaced by the index) kept as the NR+1 largest, ascending.
+    // Key order equals the (|theta|, index) order of jnp.argsort unless two entries share their upper 26 value bits; the
+    // (NR+1)-th key is kept so that such a near tie at the boundary is seen too.
+    int tk[NR + 1];
+#pragma unroll
+    for (int p = 0; p <= NR; p++) tk[p] = 0;
+#pragma unroll
+    for (int m = 0; m < nm; m++) {
+        int v = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m);
+        tk[0] = max(tk[0], v);
+#pragma unroll
+        for (int p = 0; p < NR; p++) { const int lo = min(tk[p], tk[p + 1]), hi = max(tk[p], tk[p + 1]); tk[p] = lo; tk[p + 1] = hi; }
+    }
+    int ti[NR];
+    bool near = false;
+#pragma unroll
+    for (int p = 0; p < NR; p++) { ti[p] = tk[p + 1] & 31; near |= ((tk[p] ^ tk[p + 1]) < 32); }
+    if (near) {
+        const int pkd = top_abs_exact<NR>(row);
+#pragma unroll
+        for (int p = 0; p < NR; p++) ti[p] = (pkd >> (5 * p)) & 31;
+    }
+    const float sigma = row[nm];
+    const float rinv = 1.0f / sigma;
+    const pk::f2 rinv2 = pk::dup(rinv);
+    // ---- ker_mixed row sums: rowsum_i = sum_m exp(-(D[idx_i][m] * rinv)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]
+    constexpr int NP = NR / 2;                       // pairs of reduced rows handled together
+    pk::f2 rs2[NP > 0 ? NP : 1];
+    float rsl = 0.0f;                                // last row when NR is odd
+#pragma unroll
+    for (int p = 0; p < NP; p++) rs2[p] = pk::dup(0.0f);
+    const float* Dr[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) Dr[i] = D + ti[i] * nm;        // D is symmetric bit for bit: row idx_i
+#pragma unroll 1
+    for (int m = 0; m + 1 < nm; m += 2) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const pk::f2 d0 = pk::mul2(pk::pack(Dr[2 * p][m], Dr[2 * p + 1][m]), rinv2);
+            const pk::f2 d1 = pk::mul2(pk::pack(Dr[2 * p][m + 1], Dr[2 * p + 1][m + 1]), rinv2);
+            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d0), -pk::hi(d0)));
+            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d1), -pk::hi(d1)));
+        }
+        if constexpr (NR & 1) {
+            const pk::f2 dl = pk::mul2(pk::pack(Dr[NR - 1][m], Dr[NR - 1][m + 1]), rinv2);
+            const pk::f2 e = pk::exp2_nonpos(-pk::lo(dl), -pk::hi(dl));
+            rsl = rsl + pk::lo(e); rsl = rsl + pk::hi(e);
+        }
+    }
+    if constexpr (nm & 1) {                          // last column
+        constexpr int m = nm - 1;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const pk::f2 d0 = pk::mul2(pk::pack(Dr[2 * p][m], Dr[2 * p + 1][m]), rinv2);
+            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d0), -pk::hi(d0)));
+        }
+        if constexpr (NR & 1) {
+            const float dl = Dr[NR - 1][m] * rinv;
+            rsl = rsl + pk::lo(pk::exp2_nonpos(-dl, -dl));
+        }
+    }
+    float rowsum[NR];
+#pragma unroll
+    for (int p = 0; p < NP; p++) pk::unpack(rs2[p], rowsum[2 * p], rowsum[2 * p + 1]);
+    if constexpr (NR & 1) rowsum[NR - 1] = rsl;
+    // ---- ker_red (symmetric bit for bit); diagonal exp(-(0 * rinv)) = 1
+    float K[NR][NR];
+    {
+        constexpr int NE = NR * (NR - 1) / 2;
+        float dv[NE + 1];
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            K[i][i] = 1.0f;
+#pragma unroll
+            for (int j = 0; j < i; j++) dv[e++] = -(Dr[i][ti[j]] * rinv);
+        }
+        dv[NE] = dv[NE - 1];
+        float ev[NE + 1];
+#pragma unroll
+        for (int q = 0; q < NE; q += 2) pk::unpack(pk::exp2_nonpos(dv[q], dv[q + 1]), ev[q], ev[q + 1]);
+        e = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+#pragma unroll
+            for (int j = 0; j < i; j++) { K[i][j] = ev[e]; K[j][i] = ev[e]; e++; }
+    }
+    // ---- A = ker_red + 0.05 I, Cholesky with reciprocal pivots; the two right-hand sides (kbar, 1) are solved as one packed pair
+    float Lm[NR][NR], rd[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        float acc = K[j][j] + 0.05f;
+#pragma unroll
+        for (int k = 0; k < j; k++) acc = fmaf(-Lm[j][k], Lm[j][k], acc);
+        const float dd = sqrtf(acc);
+        Lm[j][j] = dd; rd[j] = 1.0f / dd;
+#pragma unroll
+        for (int i = j + 1; i < NR; i++) {
+            float aa = K[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) aa = fmaf(-Lm[i][k], Lm[j][k], aa);
+            Lm[i][j] = aa * rd[j];
+        }
+    }
+    pk::f2 uw[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        pk::f2 ab = pk::pack(c.inv_nm * rowsum[i], 1.0f);
+#pragma unroll
+        for (int k = 0; k < i; k++) ab = pk::fma2(pk::dup(-Lm[i][k]), uw[k], ab);
+        uw[i] = pk::mul2(ab, pk::dup(rd[i]));
+    }
+#pragma unroll
+    for (int i = NR - 1; i >= 0; i--) {
+        pk::f2 ab = uw[i];
+#pragma unroll
+        for (int k = i + 1; k < NR; k++) ab = pk::fma2(pk::dup(-Lm[k][i]), uw[k], ab);
+        uw[i] = pk::mul2(ab, pk::dup(rd[i]));
+    }
+    float u[NR], w[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) pk::unpack(uw[i], u[i], w[i]);
+    float su = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NR; i++) { su = su + u[i]; sw = sw + w[i]; }
+    const float nu = (su - 1.0f) / sw;
+    float beta[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) beta[i] = fmaf(-nu, w[i], u[i]);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        float t = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NR; j++) t = fmaf(K[i][j], beta[j], t);
+        s1 = fmaf(beta[i], t, s1);
+        s2 = fmaf(c.m2_inv_nm * rowsum[i], beta[i], s2);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) beta_out[i] = beta[i];
+    int packed = 0;
+#pragma unroll
+    for (int i = 0; i < NR; i++) packed |= ti[i] << (5 * i);
+    *idx_out = packed;
+    return s1 + s2;
+}
+
+// float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order of the costs)
+__device__ __forceinline__ uint32_t sort_key32(float x) {
+    const float xz = x + 0.0f;
+    const uint32_t u = dm::f2u(xz);
+    uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (xz != xz) k = 0xffffffffu;
+    return k;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollArgs ra) {
+    extern __shared__ __align__(16) float sm[];
+    const RiskArgs& a = ra.r;
+    const int g = blockIdx.x;
+    if (g >= a.n_samples) return;
+    constexpr int nm = NR * NR, d = nm + 1;
+    static_assert(d <= 32, "one covariance row per lane");
+    constexpr int NPAIR = (d + 1) / 2;               // packed column pairs of a covariance / Cholesky row
+    const int tid = threadIdx.x, nt = ICF_THREADS, warp = tid >> 5, lane = tid & 31;
+    const int e = g / a.B, np = c.np, S = c.S_in, ne = c.n_el_in;
+    const FastLayout L = fast_layout(NR, S, ne);
+    const int ldt = L.ldt, ldc = L.ldc;
+    float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = sm + L.betas; int* idxs = (int*)(sm + L.idxs);
+    int* perm = (int*)(sm + L.perm); float* xc = sm + L.xc; float* C = sm + L.C; float* LT = C; float* mean = sm + L.mean;
+    float* small = sm + L.small;
+    const int eth_sz = al4(ne * ldt), ecost_sz = al4(ne), eb_sz = al4(ne * NR), ei_sz = al4(ne);
+#pragma unroll 1
+    for (int i = tid; i < ICF_MAX_NE * ldc; i += nt) xc[i] = 0.0f;                 // pad columns / rows stay zero
+    // ---- distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
+    {
+        float* F = th;
+        const float* Fg = ra.feat + (size_t)g * nm * 2 * NV;
+#pragma unroll 1
+        for (int i = tid; i < nm * 2 * NV; i += nt) F[i] = Fg[i];
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < nm * nm; i += nt) {
+            const float* Fa = F + (i / nm) * 2 * NV; const float* Fb = F + (i % nm) * 2 * NV;
+            float dist = 0.0f;
+#pragma unroll
+            for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
+            D[i] = dist;
+        }
+        __syncthreads();
+    }
+    // ---- iteration 0 evaluates the S rows of theta0 (a constant table); later iterations the S - ne resampled rows
+#pragma unroll 1
+    for (int i = tid; i < S * d; i += nt) th[(i / d) * ldt + (i % d)] = __ldg(c.theta0 + i);
+    // covariance task of this thread: row cr, columns 4*cg .. 4*cg+3 (lower triangle in groups of four; tasks beyond nt wrap)
+    int cr = -1, cg = 0, cr2 = -1, cg2 = 0;
+    {
+        int t = 0;
+        for (int r = 0; r < d; r++)
+            for (int q4 = 0; q4 <= r / 4; q4++) { if (t == tid) { cr = r; cg = q4; } if (t == tid + nt) { cr2 = r; cg2 = q4; } t++; }
+    }
+    __syncthreads();
+    float* resb = a.res_beta + (size_t)g * c.iters_in;
+#pragma unroll 1
+    for (int it = 0; it < c.iters_in; it++) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const int n_old = it == 0 ? 0 : ne, n_new = S - n_old;
+        float* eth_c = sm + L.eth + cur * eth_sz; float* eth_n = sm + L.eth + nxt * eth_sz;
+        float* ecost_c = sm + L.ecost + cur * ecost_sz; float* ecost_n = sm + L.ecost + nxt * ecost_sz;
+        float* eb_c = sm + L.ebetas + cur * eb_sz; float* eb_n = sm + L.ebetas + nxt * eb_sz;
+        int* ei_c = (int*)(sm + L.eidxs) + cur * ei_sz; int* ei_n = (int*)(sm + L.eidxs) + nxt * ei_sz;
+        // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
+#pragma unroll 1
+        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, th + s * ldt, D, betas + s * NR, idxs + s);
+        __syncthreads();
+        // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
+        if (warp == 0) {
+            uint32_t k0, k1, k2, k3; int j0, j1, j2, j3;
+            {
+                uint32_t kk[4]; int jj[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = lane + 32 * u;
+                    if (j < S) { kk[u] = sort_key32(j < n_old ? ecost_c[j] : cost[j - n_old]); jj[u] = j; }
+                    else { kk[u] = 0xffffffffu; jj[u] = 0x7fffffff; }
+                }
+                // stable local sort (adjacent exchanges only; indices ascend within a lane)
+#define ICF_CE(x, y) { const bool sw_ = kk[y] < kk[x]; const uint32_t ka_ = kk[x], kb_ = kk[y]; const int ja_ = jj[x], jb_ = jj[y]; \
+                       kk[x] = sw_ ? kb_ : ka_; kk[y] = sw_ ? ka_ : kb_; jj[x] = sw_ ? jb_ : ja_; jj[y] = sw_ ? ja_ : jb_; }
+                ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(2, 3) ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(0, 1)
+#undef ICF_CE
+                k0 = kk[0]; k1 = kk[1]; k2 = kk[2]; k3 = kk[3]; j0 = jj[0]; j1 = jj[1]; j2 = jj[2]; j3 = jj[3];
+            }
+            int mine = 0;
+#pragma unroll 1
+            for (int r = 0; r < ne; r++) {
+                const uint32_t m = __reduce_min_sync(FULL, k0);
+                const uint32_t wj = __reduce_min_sync(FULL, (k0 == m) ? (uint32_t)j0 : 0x7fffffffu);
+                if ((uint32_t)j0 == wj) { k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu; j0 = j1; j1 = j2; j2 = j3; j3 = 0x7fffffff; }
+                if (lane == r) mine = (int)wj;
+            }
+            if (lane < ne) {
+                perm[lane] = mine;
+                ecost_n[lane] = mine < n_old ? ecost_c[mine] : cost[mine - n_old];
+            }
+        }
+        __syncthreads();
+        // -- gather the elites (rank order), their mean and the centered rows  [compute_beta.py:56-61]
+        if (tid < d) {
+            float s = 0.0f;
+            float v[ICF_MAX_NE];
+#pragma unroll
+            for (int el = 0; el < ICF_MAX_NE; el++) {
+                if (el < ne) {
+                    const int p = perm[el];
+                    v[el] = p < n_old ? eth_c[p * ldt + tid] : th[(p - n_old) * ldt + tid];
+                    eth_n[el * ldt + tid] = v[el];
+                    s = s + v[el];
+                }
+            }
+            const float mu = s / (float)ne;
+            mean[tid] = mu;
+#pragma unroll
+            for (int el = 0; el < ICF_MAX_NE; el++) if (el < ne) xc[el * ldc + tid] = v[el] - mu;
+        } else if (tid >= 32) {
+#pragma unroll 1
+            for (int i = tid - 32; i < ne * NR; i += nt - 32) {
+                const int p = perm[i / NR], k = i % NR;
+                eb_n[i] = p < n_old ? eb_c[p * NR + k] : betas[(p - n_old) * NR + k];
+            }
+            if (tid - 32 < ne) { const int p = perm[tid - 32]; ei_n[tid - 32] = p < n_old ? ei_c[p] : idxs[p - n_old]; }
+        }
+        __syncthreads();
+        // -- jnp.cov (ddof = 1) + 0.05 I, lower triangle, four columns per task  [compute_beta.py:61]
+        {
+            const float nm1 = (float)(ne - 1);
+            int r = cr, q4 = cg;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                if (r >= 0) {
+                    pk::f2 a01 = pk::dup(0.0f), a23 = pk::dup(0.0f);
+#pragma unroll
+                    for (int el = 0; el < ICF_MAX_NE; el++) {
+                        if (el < ne) {
+                            const float xr = xc[el * ldc + r];
+                            const float4 xq = *reinterpret_cast<const float4*>(xc + el * ldc + 4 * q4);
+                            a01 = pk::fma2(pk::dup(xr), pk::pack(xq.x, xq.y), a01);
+                            a23 = pk::fma2(pk::dup(xr), pk::pack(xq.z, xq.w), a23);
+                        }
+                    }
+                    float o[4]; pk::unpack(a01, o[0], o[1]); pk::unpack(a23, o[2], o[3]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { o[u] = o[u] / nm1; if (4 * q4 + u == r) o[u] = o[u] + 0.05f; }
+                    *reinterpret_cast<float4*>(C + r * ldc + 4 * q4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                r = cr2; q4 = cg2;
+                if (r < 0) break;
+            }
+        }
+        __syncthreads();
+        // -- Cholesky by warp 0: lane i owns row i in registers, right-looking; column j goes through LT (= L transposed), which is
+        //    also what the resampling reads.  Entry (i,q) accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.
+        if (warp == 0) {
+            pk::f2 a2[NPAIR];
+            {
+                const int rowi = lane < d ? lane : d - 1;
+#pragma unroll
+                for (int p = 0; p < NPAIR; p++) { const float2 v = *reinterpret_cast<const float2*>(C + rowi * ldc + 2 * p); a2[p] = pk::pack(v.x, v.y); }
+            }
+            __syncwarp();                                 // every row is in registers before LT overwrites C
+#pragma unroll
+            for (int j = 0; j < d; j++) {
+                const float aj = (j & 1) ? pk::hi(a2[j / 2]) : pk::lo(a2[j / 2]);
+                const float ajj = __shfl_sync(FULL, aj, j);
+                const float dd = sqrtf(ajj);
+                const float rdj = 1.0f / dd;
+                const float lij = lane == j ? dd : aj * rdj;
+                if (lane >= j && lane < d) LT[j * ldc + lane] = lij;
+                __syncwarp();
+                const pk::f2 nl = pk::dup(-lij);
+                if ((j & 1) == 0 && j + 1 < d) {          // column j+1 shares the pair of column j (already final): update the upper half only
+                    const float lq = LT[j * ldc + j + 1];
+                    float x0, x1; pk::unpack(a2[j / 2], x0, x1);
+                    a2[j / 2] = pk::pack(x0, fmaf(-lij, lq, x1));
+                }
+#pragma unroll
+                for (int g4 = (j + 2) / 4; 2 * g4 < NPAIR; g4++) {     // float4 = pairs 2*g4 and 2*g4+1
+                    const float4 lq = *reinterpret_cast<const float4*>(LT + j * ldc + 4 * g4);
+                    if (2 * g4 >= (j + 2) / 2) a2[2 * g4] = pk::fma2(nl, pk::pack(lq.x, lq.y), a2[2 * g4]);
+                    if (2 * g4 + 1 < NPAIR) a2[2 * g4 + 1] = pk::fma2(nl, pk::pack(lq.z, lq.w), a2[2 * g4 + 1]);
+                }
+            }
+        }
+        __syncthreads();
+        // -- resample: one thread per new row, two columns per packed accumulator, ascending k  [compute_beta.py:63-66]
+        {
+            const int nrow = S - ne;
+            const float* zT = c.zb_iterT + (size_t)it * d * nrow;
+#pragma unroll 1
+            for (int r = tid; r < nrow; r += nt) {
+                pk::f2 acc[NPAIR];
+#pragma unroll
+                for (int p = 0; p < NPAIR; p++) acc[p] = pk::dup(0.0f);
+#pragma unroll
+                for (int k = 0; k < d; k++) {
+                    const float zk = __ldg(zT + k * nrow + r);
+                    const pk::f2 z2 = pk::dup(zk);
+                    if (k & 1) {                             // column k is the upper half of pair k/2: L[k][k] only
+                        float x0, x1; pk::unpack(acc[k / 2], x0, x1);
+                        acc[k / 2] = pk::pack(x0, fmaf(LT[k * ldc + k], zk, x1));
+                    }
+#pragma unroll
+                    for (int g4 = (k + 1) / 4; 2 * g4 < NPAIR; g4++) {
+                        const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+                        if (2 * g4 >= (k + 1) / 2) acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
+                        if (2 * g4 + 1 < NPAIR) acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
+                    }
+                }
+                float* dst = th + r * ldt;
+#pragma unroll
+                for (int p = 0; p < NPAIR; p++) {
+                    float x0, x1; pk::unpack(acc[p], x0, x1);
+                    float v0 = mean[2 * p] + x0;
+                    if (2 * p == nm) v0 = (v0 != v0) ? v0 : (v0 > c.sigma_clip ? v0 : c.sigma_clip);
+                    dst[2 * p] = v0;
+                    if (2 * p + 1 < d) {
+                        float v1 = mean[2 * p + 1] + x1;
+                        if (2 * p + 1 == nm) v1 = (v1 != v1) ? v1 : (v1 > c.sigma_clip ? v1 : c.sigma_clip);
+                        dst[2 * p + 1] = v1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            resb[it] = ecost_n[0];
+            if (it == c.iters_in - 1) {                // beta / reduced set of the best sample; sigma from the RESAMPLED array [Q7]
+                for (int i = 0; i < NR; i++) { small[i] = eb_n[i]; ((int*)small)[16 + i] = (ei_n[0] >> (5 * i)) & 31; }
+                const int p0 = perm[0];
+                small[48] = p0 < ne ? eth_n[p0 * ldt + nm] : th[(p0 - ne) * ldt + nm];
+            }
+        }
+        // the next iteration's first barrier (after the evaluation) orders these reads against later writes of perm / th
+    }
+    __syncthreads();
+    // ---- risk of the chosen reduced set (its rollouts come back from global memory)  [costs.py:173-186, 121-135]
+    const int* ridx = (const int*)small + 16;
+    const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
+    const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
+    constexpr int NW = ICF_THREADS / 32;
+    float* red = sm + L.red;
+#pragma unroll 1
+    for (int r = 0; r < NR; r++) {
+        const float* xred = xg + ridx[r] * np; const float* yred = yg + ridx[r] * np;
+        float m = 0.0f, l = 0.0f, u = 0.0f;
+        for (int i = tid; i < c.O * np; i += nt) {
+            const int o = i / np, t = i % np;
+            m = dm::nmax_(m, fbar(c, xred[t], yred[t], xo[o * T_ + t], yo[o * T_ + t]));
+        }
+        for (int t = tid; t < np; t += nt) {
+            l = dm::nmax_(l, dm::max0_(-yred[t] + c.y_lb));
+            u = dm::nmax_(u, dm::max0_(yred[t] - c.y_ub));
+        }
+        m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
+        if (lane == 0) { red[(r * 3 + 0) * NW + warp] = m; red[(r * 3 + 1) * NW + warp] = l; red[(r * 3 + 2) * NW + warp] = u; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float cs[NR], lbv[NR], ubv[NR], beta[NR];
+        for (int r = 0; r < NR; r++) {
+            float m = red[(r * 3 + 0) * NW], l = red[(r * 3 + 1) * NW], u = red[(r * 3 + 2) * NW];
+            for (int wv = 1; wv < NW; wv++) { m = dm::nmax_(m, red[(r * 3 + 0) * NW + wv]); l = dm::nmax_(l, red[(r * 3 + 1) * NW + wv]); u = dm::nmax_(u, red[(r * 3 + 2) * NW + wv]); }
+            cs[r] = m; lbv[r] = l; ubv[r] = u; beta[r] = small[r];
+            a.beta[(size_t)g * NR + r] = small[r];
+        }
+        const float sigma = small[48];
+        a.sigma[g] = sigma;
+        a.risk[g] = mmd_cost(c, beta, cs, sigma);
+        a.lane[g] = mmd_cost(c, beta, lbv, sigma) + mmd_cost(c, beta, ubv, sigma);
+    }
+}

@@ -31,6 +31,13 @@ __global__ void k_noise(DCfg c, DWork w, int n_ep, int it0, int n_it) {
         z3[i] = dr::normal_elem(k3, (uint32_t)n, (uint32_t)i);
     }
     for (int i = threadIdx.x; i < ncem; i += blockDim.x) zc[i] = dr::normal_elem(k2, (uint32_t)ncem, (uint32_t)i);   // [Q6]
+    if (c.noise_kind == 1 && w.btab) {        // candidates of the Beta rejection sampler, shared by the B samples of the episode [Q5]
+        float* bt = w.btab + slot * (size_t)(4 * GT_FIELDS) * n;
+        for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) {
+            const int stream = i / n, el = i % n;
+            dr::gamma_table_fill(dr::gamma_stream_key(k1, k2, stream), (uint32_t)n, (uint32_t)el, bt + (size_t)stream * GT_FIELDS * n + el);
+        }
+    }
     if (threadIdx.x == 0) {
         uint32_t* k = w.keys + slot * 4;
         k[0] = k1.k0; k[1] = k1.k1; k[2] = k2.k0; k[3] = k2.k1;

@@ -20,6 +20,8 @@ struct RiskArgs {
     size_t z_stride;
     const uint32_t* keys;            // episode e at keys + e*key_stride, 4 words
     size_t key_stride;
+    const float* btab;               // episode e at btab + e*btab_stride: [4][GT_FIELDS][nr*np] (beta noise; null -> direct sampler)
+    size_t btab_stride;
     const float *x_obs, *y_obs;      // [E][O][100]
     float *risk, *lane;              // [n]
     float *beta, *sigma, *res_beta;  // [n][nr], [n], [n][iters_in]
@@ -119,8 +121,15 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
         } else {
             const uint32_t* keys = a.keys + e * a.key_stride;
             dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
-            const float b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
-            const float b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+            float b1, b2;
+            if (a.btab) {
+                const float* bt = a.btab + e * a.btab_stride;
+                b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+                b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+            } else {
+                b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+                b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+            }
             pa = c.sigma_acc * (2.0f * b1 - 1.0f);
             ps = c.ksig_steer * (2.0f * b2 - 1.0f);
         }

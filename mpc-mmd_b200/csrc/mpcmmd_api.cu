@@ -11,6 +11,7 @@
 #include "../../include/mpcmmd.h"
 #include "k_project.cuh"
 #include "k_risk.cuh"
+#include "k_inner_cem.cuh"
 #include "k_select.cuh"
 
 static thread_local std::string g_err;
@@ -63,7 +64,15 @@ __global__ void k_boundary(const float* init_state, float* beq_x, float* beq_y, 
     state0[e * 5 + 4] = dm::atan2_(s[3], s[2]);
 }
 
-static size_t inner_cem_smem(const DCfg& d) { return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float); }
+// the packed-FP32 kernel (k_inner_cem.cuh) covers num_reduced^2 + 1 <= 32 with at most 128 candidates / 12 elites per inner iteration;
+// everything else runs the generic kernel of k_risk.cuh
+static bool inner_cem_is_fast(const DCfg& d) {
+    return d.nr <= 5 && d.S_in <= ICF_MAX_S && d.n_el_in <= ICF_MAX_NE && d.n_el_in >= 2 && d.S_in - d.n_el_in >= 1;
+}
+static size_t inner_cem_smem(const DCfg& d) {
+    if (inner_cem_is_fast(d)) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
+}
 // samples per CTA of k_rollouts: as many as keep one thread per rollout busy (bounded by shared memory), but never so
 // many that a small batch leaves SMs idle (latency at batch = 1 episode)
 static int roll_spb(const DCfg& d, int kind, int n_samples) {
@@ -80,8 +89,16 @@ static size_t roll_smem_for(const DCfg& d, int kind, int spb) {
 static size_t roll_smem(const DCfg& d, int kind) { return roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30)); }
 
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-static inner_cem_fn pick_inner_cem(int nr) {
-    switch (nr) {
+static inner_cem_fn pick_inner_cem(const DCfg& d) {
+    if (inner_cem_is_fast(d)) {
+        switch (d.nr) {
+            case 2: return k_inner_cem_fast<2>;
+            case 3: return k_inner_cem_fast<3>;
+            case 4: return k_inner_cem_fast<4>;
+            case 5: return k_inner_cem_fast<5>;
+        }
+    }
+    switch (d.nr) {
         case 2: return k_inner_cem<2>;
         case 3: return k_inner_cem<3>;
         case 4: return k_inner_cem<4>;
@@ -92,6 +109,7 @@ static inner_cem_fn pick_inner_cem(int nr) {
         default: return nullptr;
     }
 }
+static int inner_cem_threads(const DCfg& d) { return inner_cem_is_fast(d) ? ICF_THREADS : RISKO_THREADS; }
 
 extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle* out) {
     if (!cfg || !out) return fail("mpcmmd_create: null argument");
@@ -136,6 +154,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     AL(beta, EB * nr) AL(sigma, EB) AL(res_beta, EB * d.iters_in)
     AL(z1, (size_t)E * d.iters * n) AL(z2, (size_t)E * d.iters * n) AL(z3, (size_t)E * d.iters * n) AL(zcem, (size_t)E * d.iters * ncem)
     AL(keys, (size_t)E * d.iters * 4)
+    if (d.noise_kind == 1) { AL(btab, (size_t)E * d.iters * 4 * GT_FIELDS * n) } else w.btab = nullptr;
     AL(idx_mpc, E) AL(init_state, (size_t)E * 6) AL(mean0, (size_t)E * NPAR) AL(cov0, (size_t)E * 64)
     AL(x_obs, (size_t)E * d.O * T_) AL(y_obs, (size_t)E * d.O * T_) AL(v_des, E)
     AL(o_cx, (size_t)E * NV) AL(o_cy, (size_t)E * NV) AL(o_lane, E) AL(o_obs, E) AL(o_beta, (size_t)E * nr) AL(o_sigma, E)
@@ -187,7 +206,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
         if (rs > 48 * 1024 && cudaFuncSetAttribute(k_rollouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
     }
-    inner_cem_fn f = pick_inner_cem(nr);
+    inner_cem_fn f = pick_inner_cem(d);
     if (f) {
         if (inner_cem_smem(d) > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inner_cem_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
@@ -239,14 +258,14 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat;
     inner_cem_fn f = nullptr;
     if (opt) {
-        f = pick_inner_cem(d.nr);
+        f = pick_inner_cem(d);
         if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
     }
     k_rollouts<<<(r.n_samples + ra.spb - 1) / ra.spb, ROLL_THREADS, roll_smem_for(d, r.cost_kind, ra.spb), s>>>(d, ra);
     if (n_launch) *n_launch = 1;
     if (opt) {
-        f<<<r.n_samples, RISKO_THREADS, inner_cem_smem(d), s>>>(d, ra);
+        f<<<r.n_samples, inner_cem_threads(d), inner_cem_smem(d), s>>>(d, ra);
         if (n_launch) *n_launch = 2;
     }
     return 0;
@@ -270,6 +289,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         r.n_samples = n_ep * d.B; r.B = d.B; r.cost_kind = kind; r.acc = w.acc; r.steer = w.steer; r.state0 = h->state0;
         r.z1 = w.z1 + it * n; r.z2 = w.z2 + it * n; r.z3 = w.z3 + it * n; r.z_stride = (size_t)d.iters * n;
         r.keys = w.keys + it * 4; r.key_stride = (size_t)d.iters * 4;
+        r.btab = w.btab ? w.btab + (size_t)it * 4 * GT_FIELDS * n : nullptr; r.btab_stride = (size_t)d.iters * 4 * GT_FIELDS * n;
         r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
         int nl = 0;
         if (launch_risk(h, r, s, &nl)) return -1;
@@ -434,7 +454,7 @@ extern "C" int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const fl
     CK(cudaSetDevice(h->device));
     RiskArgs r;
     r.n_samples = n; r.B = n; r.cost_kind = cost_kind; r.acc = acc; r.steer = steer; r.state0 = state0; r.z1 = z1; r.z2 = z2; r.z3 = z3; r.z_stride = 0;
-    r.keys = keys; r.key_stride = 0; r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
+    r.keys = keys; r.key_stride = 0; r.btab = nullptr; r.btab_stride = 0; r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
     if (cost_kind == MPCMMD_COST_MMD_OPT && ensure_opt_scratch(h)) return -1;
     if (launch_risk(h, r, 0)) return -1;
     CK(cudaDeviceSynchronize());
