@@ -22,6 +22,7 @@ struct DCfg {
     float sigma_clip, inv_nm, m2_inv_nm, beta_del, sigma_random;
     const float *P, *Pd, *Pdd, *Gx, *Gy, *Kx, *Ky, *Wfit;   // device copies of the host constants
     const float *z_init, *theta0, *zb_iter;                  // constant normal tables (generated at create)
+    const float *theta0T;                                    // theta0 transposed to [column][row]
     const float *zb_iterT;                                   // zb_iter transposed to [iter][column][row] for coalesced row-per-thread reads
 };
 

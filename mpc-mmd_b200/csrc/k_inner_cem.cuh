@@ -98,35 +98,12 @@ __device__ __noinline__ int top_abs_exact(const float* __restrict__ row) {     /
     return packed;
 }
 
-// one beta sample of the inner CEM [compute_beta.py:113-129, 70-91]; bit-identical to beta_sample<NR> of k_risk.cuh
+// the QP + MMD cost of one beta sample given its reduced set (indices ti, ascending |theta|) and bandwidth sigma
+// [compute_beta.py:70-91, 120-129]; bit-identical to the second half of beta_sample<NR> of k_risk.cuh
 template <int NR>
-__device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
-                                                  float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
+__device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], float sigma, const float* __restrict__ D,
+                                           float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
     constexpr int nm = NR * NR;
-    static_assert(nm <= 32, "index must fit in the 5 low key bits");
-    // ---- top-NR |theta|: keys (|theta| bits with the 5 low bits replaced by the index) kept as the NR+1 largest, ascending.
-    // Key order equals the (|theta|, index) order of jnp.argsort unless two entries share their upper 26 value bits; the
-    // (NR+1)-th key is kept so that such a near tie at the boundary is seen too.
-    int tk[NR + 1];
-#pragma unroll
-    for (int p = 0; p <= NR; p++) tk[p] = 0;
-#pragma unroll
-    for (int m = 0; m < nm; m++) {
-        int v = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m);
-        tk[0] = max(tk[0], v);
-#pragma unroll
-        for (int p = 0; p < NR; p++) { const int lo = min(tk[p], tk[p + 1]), hi = max(tk[p], tk[p + 1]); tk[p] = lo; tk[p + 1] = hi; }
-    }
-    int ti[NR];
-    bool near = false;
-#pragma unroll
-    for (int p = 0; p < NR; p++) { ti[p] = tk[p + 1] & 31; near |= ((tk[p] ^ tk[p + 1]) < 32); }
-    if (near) {
-        const int pkd = top_abs_exact<NR>(row);
-#pragma unroll
-        for (int p = 0; p < NR; p++) ti[p] = (pkd >> (5 * p)) & 31;
-    }
-    const float sigma = row[nm];
     const float rinv = 1.0f / sigma;
     const pk::f2 rinv2 = pk::dup(rinv);
     // ---- ker_mixed row sums: rowsum_i = sum_m exp(-(D[idx_i][m] * rinv)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]
@@ -251,6 +228,37 @@ __device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __
     return s1 + s2;
 }
 
+// one beta sample of the inner CEM [compute_beta.py:113-129, 70-91]; bit-identical to beta_sample<NR> of k_risk.cuh
+template <int NR>
+__device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
+                                                  float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
+    constexpr int nm = NR * NR;
+    static_assert(nm <= 32, "index must fit in the 5 low key bits");
+    // ---- top-NR |theta|: keys (|theta| bits with the 5 low bits replaced by the index) kept as the NR+1 largest, ascending.
+    // Key order equals the (|theta|, index) order of jnp.argsort unless two entries share their upper 26 value bits; the
+    // (NR+1)-th key is kept so that such a near tie at the boundary is seen too.
+    int tk[NR + 1];
+#pragma unroll
+    for (int p = 0; p <= NR; p++) tk[p] = 0;
+#pragma unroll NR
+    for (int m = 0; m < nm; m++) {               // partially unrolled: the whole kernel's loop body has to stay inside the 32 KB instruction cache
+        int v = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m);
+        tk[0] = max(tk[0], v);
+#pragma unroll
+        for (int p = 0; p < NR; p++) { const int lo = min(tk[p], tk[p + 1]), hi = max(tk[p], tk[p + 1]); tk[p] = lo; tk[p + 1] = hi; }
+    }
+    int ti[NR];
+    bool near = false;
+#pragma unroll
+    for (int p = 0; p < NR; p++) { ti[p] = tk[p + 1] & 31; near |= ((tk[p] ^ tk[p + 1]) < 32); }
+    if (near) {
+        const int pkd = top_abs_exact<NR>(row);
+#pragma unroll
+        for (int p = 0; p < NR; p++) ti[p] = (pkd >> (5 * p)) & 31;
+    }
+    return beta_eval<NR>(c, ti, row[nm], D, beta_out, idx_out);
+}
+
 // float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order of the costs)
 __device__ __forceinline__ uint32_t sort_key32(float x) {
     const float xz = x + 0.0f;
@@ -260,8 +268,147 @@ __device__ __forceinline__ uint32_t sort_key32(float x) {
     return k;
 }
 
+
+// stable argsort of the S candidate costs, first ne entries, by ONE warp (S <= 128): candidate j < n_old is elite j (cost ecost_c[j]),
+// else new row j - n_old (cost[j - n_old]).  Each lane sorts its four candidates (j = lane + 32u, stable), then ne rounds of
+// redux.sync min pick the globally smallest (key, index).  Writes perm[0..ne) and the winners' costs.  [compute_beta.py:56]
+__device__ __forceinline__ void icf_select(int lane, int S, int n_old, int ne, const float* __restrict__ ecost_c, const float* __restrict__ cost,
+                                           int* __restrict__ perm, float* __restrict__ ecost_n) {
+    uint32_t k0, k1, k2, k3; int j0, j1, j2, j3;
+    {
+        uint32_t kk[4]; int jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = lane + 32 * u;
+            if (j < S) { kk[u] = sort_key32(j < n_old ? ecost_c[j] : cost[j - n_old]); jj[u] = j; }
+            else { kk[u] = 0xffffffffu; jj[u] = 0x7fffffff; }
+        }
+        // stable local sort (adjacent exchanges only; indices ascend within a lane)
+#define ICF_CE(x, y) { const bool sw_ = kk[y] < kk[x]; const uint32_t ka_ = kk[x], kb_ = kk[y]; const int ja_ = jj[x], jb_ = jj[y]; \
+                       kk[x] = sw_ ? kb_ : ka_; kk[y] = sw_ ? ka_ : kb_; jj[x] = sw_ ? jb_ : ja_; jj[y] = sw_ ? ja_ : jb_; }
+        ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(2, 3) ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(0, 1)
+#undef ICF_CE
+        k0 = kk[0]; k1 = kk[1]; k2 = kk[2]; k3 = kk[3]; j0 = jj[0]; j1 = jj[1]; j2 = jj[2]; j3 = jj[3];
+    }
+    int mine = 0;
+#pragma unroll 1
+    for (int r = 0; r < ne; r++) {
+        const uint32_t m = __reduce_min_sync(FULL, k0);
+        const uint32_t wj = __reduce_min_sync(FULL, (k0 == m) ? (uint32_t)j0 : 0x7fffffffu);
+        if ((uint32_t)j0 == wj) { k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu; j0 = j1; j1 = j2; j2 = j3; j3 = 0x7fffffff; }
+        if (lane == r) mine = (int)wj;
+    }
+    if (lane < ne) {
+        perm[lane] = mine;
+        ecost_n[lane] = mine < n_old ? ecost_c[mine] : cost[mine - n_old];
+    }
+}
+
+// Cholesky of the d x d covariance by ONE warp, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j
+// into row j of LT (LT[j][q] = L[q][j] for q >= j, zeros for q < j) and subtracts l_ij * LT[j][q] from A[i][q], j < q <= i.  Entry (i,q)
+// therefore accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.  Rolled on purpose (instruction cache).
+template <int d>
+__device__ __forceinline__ void icf_chol(float* __restrict__ C, int ldc, int lane) {
+    float* LT = C;
+    float* rowp = C + (lane < d ? lane : d - 1) * ldc;
+#pragma unroll 1
+    for (int j = 0; j < d; j++) {
+        const float aj = rowp[j];
+        const float ajj = __shfl_sync(FULL, aj, j);
+        const float dd = sqrtf(ajj);
+        const float rdj = 1.0f / dd;
+        const float lij = lane == j ? dd : aj * rdj;
+        if (lane < d) LT[j * ldc + lane] = lane < j ? 0.0f : lij;
+        __syncwarp();
+        if (lane > j && lane < d) {
+            const pk::f2 nl = pk::dup(-lij);
+            const float* lrow = LT + j * ldc;
+#pragma unroll 1
+            for (int g4 = (j + 1) >> 2; g4 <= (lane >> 2); g4++) {
+                const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * g4);
+                float4 v = *reinterpret_cast<float4*>(rowp + 4 * g4);
+                pk::unpack(pk::fma2(nl, pk::pack(l.x, l.y), pk::pack(v.x, v.y)), v.x, v.y);
+                pk::unpack(pk::fma2(nl, pk::pack(l.z, l.w), pk::pack(v.z, v.w)), v.z, v.w);
+                *reinterpret_cast<float4*>(rowp + 4 * g4) = v;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// one covariance task: C[r][4*q4 .. 4*q4+3] = (sum_el xc[el][r] * xc[el][q]) / (ne - 1) (+ 0.05 on the diagonal), el ascending  [compute_beta.py:61]
+__device__ __forceinline__ void icf_cov_task(const float* __restrict__ xc, float* __restrict__ C, int ldc, int ne, int r, int q4) {
+    const float nm1 = (float)(ne - 1);
+    pk::f2 a01 = pk::dup(0.0f), a23 = pk::dup(0.0f);
+#pragma unroll
+    for (int el = 0; el < ICF_MAX_NE; el++) {
+        if (el < ne) {
+            const float xr = xc[el * ldc + r];
+            const float4 xq = *reinterpret_cast<const float4*>(xc + el * ldc + 4 * q4);
+            a01 = pk::fma2(pk::dup(xr), pk::pack(xq.x, xq.y), a01);
+            a23 = pk::fma2(pk::dup(xr), pk::pack(xq.z, xq.w), a23);
+        }
+    }
+    float o[4]; pk::unpack(a01, o[0], o[1]); pk::unpack(a23, o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { o[u] = o[u] / nm1; if (4 * q4 + u == r) o[u] = o[u] + 0.05f; }
+    *reinterpret_cast<float4*>(C + r * ldc + 4 * q4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// one resampled row: acc[p] = (sum_k L[2p][k] z[k], sum_k L[2p+1][k] z[k]), k ascending  [compute_beta.py:63].  LT[k][q] = 0 for q < k, so a
+// term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in two ranges whose (static) column-group
+// sets skip most of the zero triangle.
+template <int d>
+__device__ __forceinline__ void icf_mvn_row(const float* __restrict__ LT, int ldc, const float* __restrict__ zT, int nrow, int r, pk::f2 (&acc)[2 * ((d + 3) / 4)]) {
+    constexpr int NG = (d + 3) / 4, GH = NG / 2, KH = 4 * GH;      // row k needs columns q >= k only: k >= KH touches groups >= GH
+#pragma unroll
+    for (int p = 0; p < 2 * NG; p++) acc[p] = pk::dup(0.0f);
+    const float* zp = zT + r;
+    float z0 = __ldg(zp), z1 = __ldg(zp + (d > 1 ? nrow : 0));   // the normals are fetched two steps ahead (L2 latency)
+#pragma unroll 1
+    for (int k = 0; k < KH; k++) {
+        const pk::f2 z2 = pk::dup(z0);
+        z0 = z1; z1 = __ldg(zp + (k + 2 < d ? k + 2 : d - 1) * nrow);
+#pragma unroll
+        for (int g4 = 0; g4 < NG; g4++) {
+            const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+            acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
+            acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
+        }
+    }
+#pragma unroll 1
+    for (int k = KH; k < d; k++) {
+        const pk::f2 z2 = pk::dup(z0);
+        z0 = z1; z1 = __ldg(zp + (k + 2 < d ? k + 2 : d - 1) * nrow);
+#pragma unroll
+        for (int g4 = GH; g4 < NG; g4++) {
+            const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+            acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
+            acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
+        }
+    }
+}
+// the same row, fully unrolled over k with the exact triangular group sets: ~40 % fewer executed instructions for ~450 more of code
+// (used by the CTA-per-chain kernel, whose warps run in near lockstep and share the instruction cache)
+template <int d>
+__device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ LT, int ldc, const float* __restrict__ zT, int nrow, int r, pk::f2 (&acc)[2 * ((d + 3) / 4)]) {
+    constexpr int NG = (d + 3) / 4;
+#pragma unroll
+    for (int p = 0; p < 2 * NG; p++) acc[p] = pk::dup(0.0f);
+#pragma unroll
+    for (int k = 0; k < d; k++) {
+        const pk::f2 z2 = pk::dup(__ldg(zT + k * nrow + r));
+#pragma unroll
+        for (int g4 = k / 4; g4 < NG; g4++) {
+            const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+            acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
+            acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
+        }
+    }
+}
+
 template <int NR>
-__global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
@@ -290,7 +437,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollA
         for (int i = tid; i < nm * nm; i += nt) {
             const float* Fa = F + (i / nm) * 2 * NV; const float* Fb = F + (i % nm) * 2 * NV;
             float dist = 0.0f;
-#pragma unroll
+#pragma unroll 2
             for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
             D[i] = dist;
         }
@@ -303,8 +450,11 @@ __global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollA
     int cr = -1, cg = 0, cr2 = -1, cg2 = 0;
     {
         int t = 0;
-        for (int r = 0; r < d; r++)
+#pragma unroll 1
+        for (int r = 0; r < d; r++) {
+#pragma unroll 1
             for (int q4 = 0; q4 <= r / 4; q4++) { if (t == tid) { cr = r; cg = q4; } if (t == tid + nt) { cr2 = r; cg2 = q4; } t++; }
+        }
     }
     __syncthreads();
     float* resb = a.res_beta + (size_t)g * c.iters_in;
@@ -321,36 +471,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollA
         for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, th + s * ldt, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
-        if (warp == 0) {
-            uint32_t k0, k1, k2, k3; int j0, j1, j2, j3;
-            {
-                uint32_t kk[4]; int jj[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = lane + 32 * u;
-                    if (j < S) { kk[u] = sort_key32(j < n_old ? ecost_c[j] : cost[j - n_old]); jj[u] = j; }
-                    else { kk[u] = 0xffffffffu; jj[u] = 0x7fffffff; }
-                }
-                // stable local sort (adjacent exchanges only; indices ascend within a lane)
-#define ICF_CE(x, y) { const bool sw_ = kk[y] < kk[x]; const uint32_t ka_ = kk[x], kb_ = kk[y]; const int ja_ = jj[x], jb_ = jj[y]; \
-                       kk[x] = sw_ ? kb_ : ka_; kk[y] = sw_ ? ka_ : kb_; jj[x] = sw_ ? jb_ : ja_; jj[y] = sw_ ? ja_ : jb_; }
-                ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(2, 3) ICF_CE(0, 1) ICF_CE(1, 2) ICF_CE(0, 1)
-#undef ICF_CE
-                k0 = kk[0]; k1 = kk[1]; k2 = kk[2]; k3 = kk[3]; j0 = jj[0]; j1 = jj[1]; j2 = jj[2]; j3 = jj[3];
-            }
-            int mine = 0;
-#pragma unroll 1
-            for (int r = 0; r < ne; r++) {
-                const uint32_t m = __reduce_min_sync(FULL, k0);
-                const uint32_t wj = __reduce_min_sync(FULL, (k0 == m) ? (uint32_t)j0 : 0x7fffffffu);
-                if ((uint32_t)j0 == wj) { k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu; j0 = j1; j1 = j2; j2 = j3; j3 = 0x7fffffff; }
-                if (lane == r) mine = (int)wj;
-            }
-            if (lane < ne) {
-                perm[lane] = mine;
-                ecost_n[lane] = mine < n_old ? ecost_c[mine] : cost[mine - n_old];
-            }
-        }
+        if (warp == 0) icf_select(lane, S, n_old, ne, ecost_c, cost, perm, ecost_n);
         __syncthreads();
         // -- gather the elites (rank order), their mean and the centered rows  [compute_beta.py:56-61]
         if (tid < d) {
@@ -379,90 +500,25 @@ __global__ void __launch_bounds__(ICF_THREADS, 8) k_inner_cem_fast(DCfg c, RollA
         }
         __syncthreads();
         // -- jnp.cov (ddof = 1) + 0.05 I, lower triangle, four columns per task  [compute_beta.py:61]
-        {
-            const float nm1 = (float)(ne - 1);
-            int r = cr, q4 = cg;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {
-                if (r >= 0) {
-                    pk::f2 a01 = pk::dup(0.0f), a23 = pk::dup(0.0f);
-#pragma unroll
-                    for (int el = 0; el < ICF_MAX_NE; el++) {
-                        if (el < ne) {
-                            const float xr = xc[el * ldc + r];
-                            const float4 xq = *reinterpret_cast<const float4*>(xc + el * ldc + 4 * q4);
-                            a01 = pk::fma2(pk::dup(xr), pk::pack(xq.x, xq.y), a01);
-                            a23 = pk::fma2(pk::dup(xr), pk::pack(xq.z, xq.w), a23);
-                        }
-                    }
-                    float o[4]; pk::unpack(a01, o[0], o[1]); pk::unpack(a23, o[2], o[3]);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { o[u] = o[u] / nm1; if (4 * q4 + u == r) o[u] = o[u] + 0.05f; }
-                    *reinterpret_cast<float4*>(C + r * ldc + 4 * q4) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                r = cr2; q4 = cg2;
-                if (r < 0) break;
-            }
-        }
+        if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
+        if (cr2 >= 0) icf_cov_task(xc, C, ldc, ne, cr2, cg2);
         __syncthreads();
-        // -- Cholesky by warp 0: lane i owns row i in registers, right-looking; column j goes through LT (= L transposed), which is
-        //    also what the resampling reads.  Entry (i,q) accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.
-        if (warp == 0) {
-            pk::f2 a2[NPAIR];
-            {
-                const int rowi = lane < d ? lane : d - 1;
-#pragma unroll
-                for (int p = 0; p < NPAIR; p++) { const float2 v = *reinterpret_cast<const float2*>(C + rowi * ldc + 2 * p); a2[p] = pk::pack(v.x, v.y); }
-            }
-            __syncwarp();                                 // every row is in registers before LT overwrites C
-#pragma unroll
-            for (int j = 0; j < d; j++) {
-                const float aj = (j & 1) ? pk::hi(a2[j / 2]) : pk::lo(a2[j / 2]);
-                const float ajj = __shfl_sync(FULL, aj, j);
-                const float dd = sqrtf(ajj);
-                const float rdj = 1.0f / dd;
-                const float lij = lane == j ? dd : aj * rdj;
-                if (lane >= j && lane < d) LT[j * ldc + lane] = lij;
-                __syncwarp();
-                const pk::f2 nl = pk::dup(-lij);
-                if ((j & 1) == 0 && j + 1 < d) {          // column j+1 shares the pair of column j (already final): update the upper half only
-                    const float lq = LT[j * ldc + j + 1];
-                    float x0, x1; pk::unpack(a2[j / 2], x0, x1);
-                    a2[j / 2] = pk::pack(x0, fmaf(-lij, lq, x1));
-                }
-#pragma unroll
-                for (int g4 = (j + 2) / 4; 2 * g4 < NPAIR; g4++) {     // float4 = pairs 2*g4 and 2*g4+1
-                    const float4 lq = *reinterpret_cast<const float4*>(LT + j * ldc + 4 * g4);
-                    if (2 * g4 >= (j + 2) / 2) a2[2 * g4] = pk::fma2(nl, pk::pack(lq.x, lq.y), a2[2 * g4]);
-                    if (2 * g4 + 1 < NPAIR) a2[2 * g4 + 1] = pk::fma2(nl, pk::pack(lq.z, lq.w), a2[2 * g4 + 1]);
-                }
-            }
-        }
+        // -- Cholesky by warp 0, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j into row j of
+        //    LT (LT[j][q] = L[q][j], q >= j; zeros for q < j) and subtracts l_ij * LT[j][q] from A[i][q], j < q <= i.  Entry (i,q)
+        //    therefore accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.  Rolled on purpose (instruction cache).
+        if (warp == 0) icf_chol<d>(C, ldc, lane);
         __syncthreads();
-        // -- resample: one thread per new row, two columns per packed accumulator, ascending k  [compute_beta.py:63-66]
+        // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
+        //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in
+        //    two ranges whose (static) column-group sets skip most of the zero triangle.
         {
+            constexpr int NG = (d + 3) / 4;
             const int nrow = S - ne;
             const float* zT = c.zb_iterT + (size_t)it * d * nrow;
 #pragma unroll 1
             for (int r = tid; r < nrow; r += nt) {
-                pk::f2 acc[NPAIR];
-#pragma unroll
-                for (int p = 0; p < NPAIR; p++) acc[p] = pk::dup(0.0f);
-#pragma unroll
-                for (int k = 0; k < d; k++) {
-                    const float zk = __ldg(zT + k * nrow + r);
-                    const pk::f2 z2 = pk::dup(zk);
-                    if (k & 1) {                             // column k is the upper half of pair k/2: L[k][k] only
-                        float x0, x1; pk::unpack(acc[k / 2], x0, x1);
-                        acc[k / 2] = pk::pack(x0, fmaf(LT[k * ldc + k], zk, x1));
-                    }
-#pragma unroll
-                    for (int g4 = (k + 1) / 4; 2 * g4 < NPAIR; g4++) {
-                        const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
-                        if (2 * g4 >= (k + 1) / 2) acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
-                        if (2 * g4 + 1 < NPAIR) acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
-                    }
-                }
+                pk::f2 acc[2 * NG];
+                icf_mvn_row_unrolled<d>(LT, ldc, zT, nrow, r, acc);
                 float* dst = th + r * ldt;
 #pragma unroll
                 for (int p = 0; p < NPAIR; p++) {

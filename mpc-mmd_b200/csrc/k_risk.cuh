@@ -95,6 +95,7 @@ struct RollArgs {
     int R;                   // rollouts per sample (nr or nr*nr)
     float *xroll, *yroll;    // [n][R][np]   (mmd_opt only)
     float* feat;             // [n][nm][22]  (mmd_opt only)
+    float* stash;            // [persistent CTAs][S][32]  row stash of k_inner_cem_warp
 };
 __host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 48); }
 

@@ -12,6 +12,7 @@
 #include "k_project.cuh"
 #include "k_risk.cuh"
 #include "k_inner_cem.cuh"
+#include "k_inner_cem_warp.cuh"
 #include "k_select.cuh"
 
 static thread_local std::string g_err;
@@ -28,6 +29,9 @@ struct mpcmmd_handle_s {
     DWork w;
     float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
     float *xroll = nullptr, *yroll = nullptr, *feat = nullptr;     // mmd_opt scratch (ensure_opt_scratch)
+    float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
+    int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
+    int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic (MPCMMD_INNER_CEM=auto|warp|cta|generic)
     int E = 0;
     std::vector<void*> allocs;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
@@ -69,10 +73,6 @@ __global__ void k_boundary(const float* init_state, float* beq_x, float* beq_y, 
 static bool inner_cem_is_fast(const DCfg& d) {
     return d.nr <= 5 && d.S_in <= ICF_MAX_S && d.n_el_in <= ICF_MAX_NE && d.n_el_in >= 2 && d.S_in - d.n_el_in >= 1;
 }
-static size_t inner_cem_smem(const DCfg& d) {
-    if (inner_cem_is_fast(d)) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
-    return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
-}
 // samples per CTA of k_rollouts: as many as keep one thread per rollout busy (bounded by shared memory), but never so
 // many that a small batch leaves SMs idle (latency at batch = 1 episode)
 static int roll_spb(const DCfg& d, int kind, int n_samples) {
@@ -89,14 +89,13 @@ static size_t roll_smem_for(const DCfg& d, int kind, int spb) {
 static size_t roll_smem(const DCfg& d, int kind) { return roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30)); }
 
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-static inner_cem_fn pick_inner_cem(const DCfg& d) {
-    if (inner_cem_is_fast(d)) {
-        switch (d.nr) {
-            case 2: return k_inner_cem_fast<2>;
-            case 3: return k_inner_cem_fast<3>;
-            case 4: return k_inner_cem_fast<4>;
-            case 5: return k_inner_cem_fast<5>;
-        }
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3 };
+static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
+    if (kind == INNER_WARP) switch (d.nr) {
+        case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
+    }
+    if (kind == INNER_CTA) switch (d.nr) {
+        case 2: return k_inner_cem_fast<2>; case 3: return k_inner_cem_fast<3>; case 4: return k_inner_cem_fast<4>; case 5: return k_inner_cem_fast<5>;
     }
     switch (d.nr) {
         case 2: return k_inner_cem<2>;
@@ -109,7 +108,11 @@ static inner_cem_fn pick_inner_cem(const DCfg& d) {
         default: return nullptr;
     }
 }
-static int inner_cem_threads(const DCfg& d) { return inner_cem_is_fast(d) ? ICF_THREADS : RISKO_THREADS; }
+static size_t inner_cem_smem_kind(const DCfg& d, int kind) {
+    if (kind == INNER_WARP) return (size_t)warp_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    if (kind == INNER_CTA) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
+}
 
 extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle* out) {
     if (!cfg || !out) return fail("mpcmmd_create: null argument");
@@ -197,7 +200,10 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         float* zbT;
         if (dalloc(h, &zbT, (size_t)d.iters_in * (S - ne) * dd)) { mpcmmd_destroy(h); return -1; }
         k_transpose_tables<<<64, 256>>>(zb, zbT, d.iters_in, S - ne, dd);
-        d.z_init = z_init; d.theta0 = theta0; d.zb_iter = zb; d.zb_iterT = zbT;
+        float* th0T;
+        if (dalloc(h, &th0T, (size_t)S * dd)) { mpcmmd_destroy(h); return -1; }
+        k_transpose_tables<<<64, 256>>>(theta0, th0T, 1, S, dd);
+        d.z_init = z_init; d.theta0 = theta0; d.theta0T = th0T; d.zb_iter = zb; d.zb_iterT = zbT;
     }
     // opt-in shared memory sizes
     if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
@@ -206,10 +212,25 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
         if (rs > 48 * 1024 && cudaFuncSetAttribute(k_rollouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
     }
-    inner_cem_fn f = pick_inner_cem(d);
-    if (f) {
-        if (inner_cem_smem(d) > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inner_cem_smem(d)) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
+    {
+        const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
+        h->inner_mode = !mode ? 0 : !strcmp(mode, "warp") ? INNER_WARP : !strcmp(mode, "cta") ? INNER_CTA : !strcmp(mode, "generic") ? INNER_GENERIC : 0;
+        if (!inner_cem_is_fast(d) && (h->inner_mode == INNER_WARP || h->inner_mode == INNER_CTA)) h->inner_mode = INNER_GENERIC;
+        for (int kind = INNER_WARP; kind <= INNER_GENERIC; kind++) {
+            if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
+            inner_cem_fn f = inner_cem_kernel(d, kind);
+            if (!f) continue;
+            const size_t sm = inner_cem_smem_kind(d, kind);
+            if (sm > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
+            if (kind == INNER_WARP) {
+                cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                int per_sm = 0, sms = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+                h->warp_grid = per_sm * (sms > 0 ? sms : 1);
+            }
+        }
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CK(cudaDeviceSynchronize());
@@ -247,6 +268,7 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (h->xroll) return 0;
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
     if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
+    if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
     return 0;
 }
 // rollouts (+ risk for the num_reduced-rollout costs); mmd_opt continues with the inner CEM kernel.  Returns launches issued.
@@ -255,17 +277,26 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat;
+    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr;
     inner_cem_fn f = nullptr;
+    int kind = INNER_GENERIC;
     if (opt) {
-        f = pick_inner_cem(d);
+        // default: one 3-warp CTA per chain (k_inner_cem_fast).  The warp-per-chain persistent kernel is kept as an opt-in
+        // (MPCMMD_INNER_CEM=warp): measured 233 ms vs 209 ms per 200-episode mmd_opt solve on B200 (profiles/r01_v7_summary.md) --
+        // 19 independent instruction streams per SM thrash the 32 KB instruction cache.
+        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : INNER_CTA;
+        if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
+        f = inner_cem_kernel(d, kind);
         if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
+        ra.stash = h->stash;
     }
     k_rollouts<<<(r.n_samples + ra.spb - 1) / ra.spb, ROLL_THREADS, roll_smem_for(d, r.cost_kind, ra.spb), s>>>(d, ra);
     if (n_launch) *n_launch = 1;
     if (opt) {
-        f<<<r.n_samples, inner_cem_threads(d), inner_cem_smem(d), s>>>(d, ra);
+        const size_t sm = inner_cem_smem_kind(d, kind);
+        if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
+        else f<<<r.n_samples, kind == INNER_CTA ? ICF_THREADS : RISKO_THREADS, sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
     }
     return 0;

@@ -178,6 +178,49 @@ def test_stage_select_bit_exact(mods):
         assert g[3] == r[3]["sel"]
 
 
+# ---- the three inner-CEM kernels (k_inner_cem_warp: one warp per chain, persistent; k_inner_cem_fast: one CTA per chain; k_inner_cem: generic)
+@pytest.mark.parametrize("mode", ["warp", "cta", "generic"])
+@pytest.mark.parametrize("nr,npr,noise,small", [(5, 30, "gaussian", True), (5, 50, "beta", False), (4, 20, "gaussian", True), (3, 20, "beta", True), (2, 25, "gaussian", True)])
+def test_inner_cem_kernel_variants_bit_exact(mods, monkeypatch, mode, nr, npr, noise, small):
+    monkeypatch.setenv("MPCMMD_INNER_CEM", mode)
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=4) if small else {}          # small=False: reference sizes (100 samples, 20 iterations, 11 elites)
+    prob, ora = _pair(mods, (nr, 3, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), **kw)
+    rng = np.random.default_rng(17 + nr)
+    n = 9
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(777, 2)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(3, 2)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    xo = xo.copy(); xo[0] = np.linspace(2, 60, 100); yo = yo.copy(); yo[0] = 1.75
+    got = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(got[k][i], ref[k], f"{mode} nr={nr} chain {i} {k}")
+
+
+def test_inner_cem_warp_persistent_grid_strides_over_chains(mods, monkeypatch):
+    """more chains than persistent CTAs (SMs x resident warps): every CTA of k_inner_cem_warp runs several chains and reuses its stash"""
+    monkeypatch.setenv("MPCMMD_INNER_CEM", "warp")
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=3)
+    prob, ora = _pair(mods, (5, 2, 0.1, 20, "gaussian", 0.0, 0.0), max_episodes=80, **kw)
+    rng = np.random.default_rng(23)
+    base_acc, base_steer = _controls(ora, rng, 16)
+    n = 7000
+    pick = rng.integers(0, 16, n)
+    acc = (base_acc[pick] * rng.uniform(0.5, 1.5, (n, 1))).astype(f32); steer = (base_steer[pick] * rng.uniform(0.5, 1.5, (n, 1))).astype(f32)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(31, 5)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(2, 1)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    got = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+    for i in list(range(0, n, 97)) + [n - 1]:
+        ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(got[k][i], ref[k], f"chain {i} {k}")
+
+
 def _episodes(O, ora, n, nobs):
     eps = [O.static_episode(nobs, k) for k in range(n)]
     tr = [ora.compute_obs_trajectories(*sc) for sc, _ in eps]
