@@ -63,7 +63,7 @@ def make_cpu_arm():
     return ora, O, cores
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -82,7 +82,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample_per_step": "1 episode x 2 costs"},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -120,6 +120,16 @@ class ClockSampler:
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout), so everything
+    # except the final line is routed to stderr: fd 1 is pointed at fd 2 for the run and the line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -128,22 +138,26 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    import __graft_entry__ as G
-    G.build()
-    from mpcmmd_b200 import CEM, cem_impl, scenes
-
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as G
+    if local == 0:
+        G.build()                      # one builder per node; the other ranks wait, then only load
+    if world > 1:
+        dist.barrier()
+    if local != 0:
+        G.build()
+    from mpcmmd_b200 import CEM, cem_impl, scenes
     W, K, E = max(args.warmup, 3), args.steps, EPISODES
 
     prob = CEM(*cem_args(), variant="static", max_episodes=E, device=local)
@@ -259,7 +273,8 @@ def main():
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); p1.solve_batch_device(cost, *[one[k] for k in keys]); b.record(); torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
-            lat[cost] = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95))}
+            lat[cost] = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)),
+                         "ms_by_kernel_ungraphed": p1.profile_solve(cost, 1)["ms"]}
         del p1
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
@@ -280,8 +295,9 @@ def main():
                            "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
                 "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat, "clocks": clk.summary()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

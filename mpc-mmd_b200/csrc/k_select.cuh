@@ -35,26 +35,37 @@ __device__ __forceinline__ bool sel_before(float rj, float nj, int j, float ri, 
     return j < i;
 }
 
+// float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order)
+__device__ __forceinline__ uint32_t sel_key32(float x) {
+    const float xz = x + 0.0f;
+    const uint32_t u = dm::f2u(xz);
+    uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (xz != xz) k = 0xffffffffu;
+    return k;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
-    extern __shared__ float sm[];                  // risk[B], res[B]
+    extern __shared__ __align__(16) float sm[];    // 64-bit composite keys [B]
     const int e = blockIdx.x;
     if (e >= a.n_ep) return;
     const int B = a.B, tid = threadIdx.x, n20 = c.n_el_cost, n5 = c.n_el;
-    float* srisk = sm; float* sres = sm + B;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);
     __shared__ int top[32], el[8];
-    __shared__ float cost20[32], th[8][NPAR], L[NPAR * NPAR], mean_new[NPAR];
+    __shared__ float cost20[32], th[8][NPAR], L[NPAR * NPAR], mean_new[NPAR], wts[8], s_sumw;
     __shared__ int s_sel;
     const float* risk = a.risk + (size_t)e * B; const float* res = a.res_norm + (size_t)e * B;
-    for (int i = tid; i < B; i += SEL_THREADS) { srisk[i] = risk[i]; sres[i] = res[i]; }
+    // position of sample i after the two stable argsorts = rank of (risk, res_norm, index): one 64-bit compare per pair
+    for (int i = tid; i < B; i += SEL_THREADS) skey[i] = ((unsigned long long)sel_key32(risk[i]) << 32) | (unsigned long long)sel_key32(res[i]);
     __syncthreads();
-    for (int i = tid; i < B; i += SEL_THREADS) {   // position of sample i after the two stable argsorts
-        const float ri = srisk[i], ni = sres[i];
+    for (int i = tid; i < B; i += SEL_THREADS) {
+        const unsigned long long ki = skey[i];
         int rank = 0;
-        for (int j = 0; j < B; j++) rank += sel_before(srisk[j], sres[j], j, ri, ni, i) ? 1 : 0;
+#pragma unroll 4
+        for (int j = 0; j < B; j++) { const unsigned long long kj = skey[j]; rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0; }
         if (rank < n20) top[rank] = i;
     }
     __syncthreads();
-    if (tid < n20) cost20[tid] = a.cost_base[(size_t)e * B + top[tid]] + a.w_obs * srisk[top[tid]];   // [cem_helper.py:253-261]
+    if (tid < n20) cost20[tid] = a.cost_base[(size_t)e * B + top[tid]] + a.w_obs * risk[top[tid]];   // [cem_helper.py:253-261]
     __syncthreads();
     if (tid < n20) {                               // stable argsort of the 20 costs -> 5 elites  [cem_helper.py:264-271]
         const float v = cost20[tid];
@@ -65,34 +76,51 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
     __syncthreads();
     float* params = a.params + (size_t)e * B * NPAR;
     if (tid < n5 * NPAR) th[tid / NPAR][tid % NPAR] = params[top[el[tid / NPAR]] * NPAR + tid % NPAR];
-    __syncthreads();
-    if (tid == 0) {                                // compute_shifted_samples  [cem_helper.py:280-291]
-        float ce[8], w[8], dif[8][NPAR];
+    // compute_shifted_samples  [cem_helper.py:280-291]: weights (one thread: 5 exps, sequential sum), then mean / covariance in parallel
+    if (tid == 0) {
+        float ce[8];
         for (int k = 0; k < n5; k++) ce[k] = cost20[el[k]];
         float wmin = ce[0]; int imin = 0;
         for (int k = 1; k < n5; k++) if (ce[k] < wmin) { wmin = ce[k]; imin = k; }
         float sum_w = 0.0f;
-        for (int k = 0; k < n5; k++) { w[k] = dm::exp_((-c.lam_inv) * (ce[k] - wmin)); sum_w = sum_w + w[k]; }
-        float* mean = a.mean + e * NPAR; float* cov = a.cov + e * NPAR * NPAR;
-        for (int i = 0; i < NPAR; i++) {
-            float s = 0.0f;
-            for (int k = 0; k < n5; k++) s = s + th[k][i] * w[k];
-            mean_new[i] = c.one_m_alpha_mean * mean[i] + c.alpha_mean * (s / sum_w);
-        }
-        for (int k = 0; k < n5; k++) for (int i = 0; i < NPAR; i++) dif[k][i] = th[k][i] - mean_new[i];
-        for (int i = 0; i < NPAR; i++)
-            for (int j = 0; j < NPAR; j++) {
-                float s = 0.0f;
-                for (int k = 0; k < n5; k++) s = s + w[k] * (dif[k][i] * dif[k][j]);
-                float v = c.one_m_alpha_cov * cov[i * NPAR + j] + c.alpha_cov * (s / sum_w);
-                v = (i == j) ? v + 0.01f : v;
-                L[i * NPAR + j] = v;
-            }
-        for (int i = 0; i < NPAR; i++) mean[i] = mean_new[i];
-        for (int i = 0; i < NPAR * NPAR; i++) cov[i] = L[i];
-        float rd[NPAR];
-        chol_serial(L, NPAR, NPAR, rd);
+        for (int k = 0; k < n5; k++) { const float w = dm::exp_((-c.lam_inv) * (ce[k] - wmin)); wts[k] = w; sum_w = sum_w + w; }
+        s_sumw = sum_w;
         s_sel = top[imin];                         // [Q1] idx_min of the 5 sorted costs applied to the 20 risk-sorted rows
+    }
+    __syncthreads();
+    float* mean = a.mean + e * NPAR; float* cov = a.cov + e * NPAR * NPAR;
+    if (tid < NPAR) {
+        float sacc = 0.0f;
+        for (int k = 0; k < n5; k++) sacc = sacc + th[k][tid] * wts[k];
+        mean_new[tid] = c.one_m_alpha_mean * mean[tid] + c.alpha_mean * (sacc / s_sumw);
+    }
+    __syncthreads();
+    if (tid < NPAR * NPAR) {
+        const int i = tid / NPAR, j = tid % NPAR;
+        float sacc = 0.0f;
+        for (int k = 0; k < n5; k++) sacc = sacc + wts[k] * ((th[k][i] - mean_new[i]) * (th[k][j] - mean_new[j]));
+        float v = c.one_m_alpha_cov * cov[tid] + c.alpha_cov * (sacc / s_sumw);
+        v = (i == j) ? v + 0.01f : v;
+        L[tid] = v;
+        cov[tid] = v;
+    }
+    if (tid < NPAR) mean[tid] = mean_new[tid];
+    __syncthreads();
+    // Cholesky of the 8x8 covariance by 8 lanes of warp 0, left-looking; same operation order per entry as chol_serial
+    if (tid < 32) {
+        const int i = tid < NPAR ? tid : NPAR - 1;
+#pragma unroll 1
+        for (int j = 0; j < NPAR; j++) {
+            float acc = L[i * NPAR + j];
+            for (int k = 0; k < j; k++) acc = fmaf(-L[i * NPAR + k], L[j * NPAR + k], acc);
+            const float ajj = __shfl_sync(FULL, acc, j);
+            const float dd = sqrtf(ajj);
+            const float rd = 1.0f / dd;
+            __syncwarp();
+            if (tid == j) L[j * NPAR + j] = dd;
+            else if (tid > j && tid < NPAR) L[tid * NPAR + j] = acc * rd;
+            __syncwarp();
+        }
     }
     __syncthreads();
     // next batch = [elites ; mean + L z]  [cem_helper.py:292-312]
@@ -102,7 +130,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
     const int s = s_sel;
     const size_t gs = (size_t)e * B + s;
     if (tid < NV) { a.o_cx[e * NV + tid] = a.cx[gs * NV + tid]; a.o_cy[e * NV + tid] = a.cy[gs * NV + tid]; }
-    if (tid == 0) { a.o_lane[e] = a.lane[gs]; a.o_obs[e] = srisk[s]; a.o_sigma[e] = a.sigma[gs]; a.o_sel[e * a.sel_stride + a.it] = s; }
+    if (tid == 0) { a.o_lane[e] = a.lane[gs]; a.o_obs[e] = risk[s]; a.o_sigma[e] = a.sigma[gs]; a.o_sel[e * a.sel_stride + a.it] = s; }
     if (tid < a.nr) a.o_beta[e * a.nr + tid] = a.beta[gs * a.nr + tid];
     if (tid < a.iters_in) a.o_res_beta[e * a.iters_in + tid] = a.res_beta[gs * a.iters_in + tid];
 }
