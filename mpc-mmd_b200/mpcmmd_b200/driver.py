@@ -1,4 +1,5 @@
-"""Sweep driver: the reference's `synthetic_static_obs/main_mpc.py` workflow on the batched B200 solver.
+"""Sweep driver: the reference's `synthetic_static_obs/main_mpc.py` and `synthetic_dynamic_obs/main_mpc.py` workflows on the
+batched B200 solver (`--variant static|dynamic`; the two drop-in `main_mpc.py` files fix it).
 
 Same command line, same loop nest (`noises x noise_levels x num_prime x num_obs x num_reduced_sets x costs`,
 main_mpc.py:77-104), same scenes (`compute_obs_data`, :10-21), same per-episode `idx_mpc` draw (:113-119), same
@@ -6,6 +7,7 @@ acceptance thresholds (:86-97) and the same on-disk schema (:130-135):
 
     ./data/{noise}_noise/noise_{int(100*level)}/ts_{num_prime}/{cost}_{num_reduced}_samples_{num_obs}_obs.npz
         cx, cy (n_acc, 11); init_state (n_acc, 6); x_obs, y_obs, vx_obs, vy_obs (n_acc, num_obs)      -- float64, accepted episodes only
+        dynamic variant adds psi_obs (n_acc, num_obs), x_obs_traj, y_obs_traj (n_acc, num_obs, 100)      (D/main_mpc.py:150-156)
 
 What differs from the reference: the 200 episodes of a sweep point are solved in ONE `solve_batch` call (they are
 independent: every input depends only on (k, num_obs)), optionally sharded over ranks (`episodes k = rank, rank+W, ...`;
@@ -57,20 +59,29 @@ def pack_records(episodes, out):
 
 
 def assemble(records, num_obs, threshold_obs, variant="static"):
-    """rank-0 side of the sweep point: sort the gathered records by episode, apply the acceptance filter of main_mpc.py:121-128
-    in episode order and build the arrays the reference saves"""
+    """rank-0 side of the sweep point: sort the gathered records by episode, apply the acceptance filter of S/main_mpc.py:121-128
+    (D/main_mpc.py:137-148) in episode order and build the arrays the reference saves"""
     rec = records[np.argsort(records[:, 0], kind="stable")]
     init_state, _, _, _ = scenes.driver_inputs(variant)
     keep = [r for r in rec if r[1] <= threshold_obs]
     cx = np.zeros((0, 11)); cy = np.zeros((0, 11)); ist = np.zeros((0, 6))
     xo = np.zeros((0, num_obs)); yo = np.zeros((0, num_obs)); vxo = np.zeros((0, num_obs)); vyo = np.zeros((0, num_obs))
+    pso = np.zeros((0, num_obs)); xt_all = np.zeros((0, num_obs, 100)); yt_all = np.zeros((0, num_obs, 100))
     for r in keep:
-        (x, y, vx, vy, _), _ = scenes.static_scene(num_obs, int(r[0]))
+        if variant == "dynamic":
+            (x, y, vx, vy, psi), _, xt, yt = scenes.dynamic_scene(num_obs, int(r[0]))
+            pso = np.append(pso, psi.reshape(1, -1), axis=0)
+            xt_all = np.append(xt_all, xt.reshape(1, num_obs, -1), axis=0); yt_all = np.append(yt_all, yt.reshape(1, num_obs, -1), axis=0)
+        else:
+            (x, y, vx, vy, _), _ = scenes.static_scene(num_obs, int(r[0]))
         cx = np.append(cx, r[3:14].reshape(1, -1), axis=0); cy = np.append(cy, r[14:25].reshape(1, -1), axis=0)
         ist = np.append(ist, np.asarray(init_state).reshape(1, -1), axis=0)
         xo = np.append(xo, x.reshape(1, -1), axis=0); yo = np.append(yo, y.reshape(1, -1), axis=0)
         vxo = np.append(vxo, vx.reshape(1, -1), axis=0); vyo = np.append(vyo, vy.reshape(1, -1), axis=0)
-    return dict(cx=cx, cy=cy, init_state=ist, x_obs=xo, y_obs=yo, vx_obs=vxo, vy_obs=vyo)
+    out = dict(cx=cx, cy=cy, init_state=ist, x_obs=xo, y_obs=yo, vx_obs=vxo, vy_obs=vyo)
+    if variant == "dynamic":
+        out.update(psi_obs=pso, x_obs_traj=xt_all, y_obs_traj=yt_all)
+    return out
 
 
 def data_path(root, noise, noise_level, num_prime, cost, num_reduced, num_obs):
@@ -88,8 +99,8 @@ def run_sweep(args, rank=0, world=1, gather=None, device=0, log=print):
                     for num_reduced in args.num_reduced_sets:
                         mine = shard(args.num_configs, rank, world)
                         prob = CEM(num_reduced, num_obs, noise_level, num_prime, noise, args.acc_const_noise, args.steer_const_noise,
-                                   variant="static", max_episodes=max(len(mine), 1), device=device)
-                        batch = scenes.static_batch(prob, mine)
+                                   variant=args.variant, max_episodes=max(len(mine), 1), device=device)
+                        batch = scenes.static_batch(prob, mine, args.variant)
                         for cost in args.costs:
                             _, threshold_obs = thresholds(prob, cost)
                             t0 = time.time()
@@ -98,7 +109,7 @@ def run_sweep(args, rank=0, world=1, gather=None, device=0, log=print):
                             if gather is not None:
                                 rec = gather(rec)
                             if rank == 0:
-                                arrays = assemble(rec, num_obs, threshold_obs)
+                                arrays = assemble(rec, num_obs, threshold_obs, args.variant)
                                 path = data_path(args.root, noise, noise_level, num_prime, cost, num_reduced, num_obs)
                                 os.makedirs(os.path.dirname(path), exist_ok=True)
                                 np.savez(path, **arrays)
@@ -134,11 +145,14 @@ def build_parser():
     p.add_argument("--steer_const_noise", type=float, required=True)
     p.add_argument("--num_configs", type=int, default=200, help="episodes per sweep point (main_mpc.py:76)")
     p.add_argument("--root", type=str, default="./data")
+    p.add_argument("--variant", type=str, default="static", choices=["static", "dynamic"])
     return p
 
 
-def main(argv=None):
+def main(argv=None, variant=None):
     args = build_parser().parse_args(argv)
+    if variant is not None:
+        args.variant = variant
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     gather = None
     if world > 1:

@@ -6,4 +6,4 @@ sys.path.insert(1, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from mpcmmd_b200.driver import main  # noqa: E402
 
 if __name__ == "__main__":
-    main()
+    main(variant="static")

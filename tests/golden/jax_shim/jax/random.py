@@ -50,3 +50,30 @@ def beta(key, a, b, shape=None, dtype=f32):
     shape = tuple(shape) if shape is not None else np.broadcast_shapes(a.shape, b.shape)
     aa = np.ascontiguousarray(np.broadcast_to(a, shape), f32).ravel(); bb = np.ascontiguousarray(np.broadcast_to(b, shape), f32).ravel()
     return asarr(np.asarray(_O.beta(_k(key), aa, bb), f32).reshape(shape))
+
+
+def _random_bits(key, n):
+    return np.asarray(_O.bits(_k(key), int(n)), np.uint32)
+
+
+def _shuffle(key, x):
+    """jax/_src/random.py::_shuffle of 0.3.23: ceil(3 ln(n) / ln(2^32 - 1)) rounds of sort-by-random-bits (stable)"""
+    x = np.asarray(down(np.asarray(x)))
+    rounds = int(np.ceil(3 * np.log(max(1, x.size)) / np.log(np.iinfo(np.uint32).max)))
+    for _ in range(rounds):
+        ks = np.asarray(split(key, 2))
+        key, sub = ks[0], ks[1]
+        x = x[np.argsort(_random_bits(sub, x.size), kind="stable")]
+    return x
+
+
+def permutation(key, x):
+    if np.ndim(x) == 0:
+        x = np.arange(int(x), dtype=np.int32)
+    return asarr(_shuffle(key, x))
+
+
+def choice(key, a, shape=(), replace=True, p=None):
+    assert p is None and not replace, "only the form the reference's scene generator uses"
+    n = int(np.prod(shape)) if len(shape) else 1
+    return asarr(_shuffle(key, a)[:n].reshape(shape))

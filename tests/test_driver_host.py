@@ -100,3 +100,44 @@ def test_episode_sharding_gloo(driver):
     assert all(p.exitcode == 0 for p in ps)
     assert shape == (7, 26)
     assert order == [1.0, 2.0, 4.0, 5.0]                    # episodes 0..6 minus the rejected multiples of 3, in episode order
+
+
+# ---- dynamic variant: scene generator + .npz schema --------------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dynamic_scenes.npz")
+
+
+@pytest.mark.parametrize("num_obs,k", [(6, 0), (6, 1), (6, 17), (6, 199), (3, 5), (2, 42)])
+def test_dynamic_scene_matches_reference_generator(driver, num_obs, k):
+    """scenes.dynamic_scene vs the reference's own obs_data class run on the JAX shim (tests/golden/make_golden_scenes.py).
+    Initial states and idx_mpc are integer/bit-level work (Threefry bits + stable sort): exact.  Trajectories come out of a constant
+    KKT solve (float32 LU in the reference, float64 inverse here): 2e-4 absolute on positions up to 150 m (= float32 round-off)."""
+    from mpcmmd_b200 import scenes
+    g = np.load(GOLD)
+    tag = f"o{num_obs}_k{k}_"
+    (x, y, vx, vy, psi), idx, xt, yt = scenes.dynamic_scene(num_obs, k)
+    assert np.array_equal(x, g[tag + "x"]) and np.array_equal(vx, g[tag + "vx"]) and np.array_equal(y, g[tag + "y"])
+    assert not vy.any() and not psi.any() and idx == int(g[tag + "idx"])
+    assert np.abs(xt - g[tag + "xt"]).max() < 2e-4 and np.abs(yt - g[tag + "yt"]).max() < 2e-4
+    assert xt.dtype == np.float32 and xt.shape == (num_obs, 100)
+
+
+def test_host_jax_rng_matches_oracle(driver):
+    """mpcmmd_b200.jaxrng (product-side scene RNG) vs the oracle's restatement of the same protocol, incl. the documented known answers"""
+    from mpcmmd_b200 import jaxrng
+    from oracle import oracle as O
+    assert jaxrng.split(jaxrng.prng_key(0), 2).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]      # JAX PRNG docs
+    assert jaxrng.threefry2x32((0x13198a2e, 0x03707344), np.uint32(0x243f6a88), np.uint32(0x85a308d3)) == (0xc4923a9c, 0x483df7a0)   # Random123 KAT
+    for seed in (0, 5, 123, 43 * 199 + 11 * 5 + 5):
+        for n in (1, 7, 30):
+            assert np.array_equal(jaxrng.bits(jaxrng.prng_key(seed), n), O.bits(O.prng_key(seed), n))
+            assert np.allclose(jaxrng.normal(jaxrng.prng_key(seed), n), O.normal(O.prng_key(seed), n), rtol=0, atol=5e-7)
+
+
+def test_assemble_dynamic_schema(driver):
+    eps = [4, 1, 2]
+    rec = driver.pack_records(eps, _fake_out(eps))
+    arrays = driver.assemble(rec, 3, 1e-5, "dynamic")
+    assert set(arrays) == {"cx", "cy", "init_state", "x_obs", "y_obs", "vx_obs", "vy_obs", "psi_obs", "x_obs_traj", "y_obs_traj"}     # D/main_mpc.py:150-156
+    assert arrays["x_obs_traj"].shape == (3, 3, 100) and arrays["psi_obs"].shape == (3, 3)
+    assert arrays["init_state"][0].tolist() == [0.0, -1.75, 5.0, 0.0, 0.0, 0.0]                                    # D/main_mpc.py:34-42
+    assert arrays["cx"][:, 0].tolist() == [1.0, 2.0, 4.0]

@@ -287,3 +287,36 @@ def test_drop_in_module_surface(mods):
         assert x.shape == (2, 100) and abs(x[0, -1] - 45.0) < 1e-4
     finally:
         sys.path.remove(root); sys.modules.pop("optimizer", None); sys.modules.pop("optimizer.cem", None)
+
+
+@pytest.mark.parametrize("variant,num_obs,num_prime,noise", [("static", 4, 50, "beta"), ("dynamic", 3, 30, "gaussian")])
+def test_sweep_driver_writes_reference_schema(mods, tmp_path, variant, num_obs, num_prime, noise):
+    """mpcmmd_b200.driver (= main_mpc.py of the two variants): 4 episodes of a cvar sweep point, full solver sizes.  The saved arrays
+    must equal the oracle's solve of every accepted episode, in episode order, with the reference's file name and keys."""
+    cem_impl, O = mods
+    from mpcmmd_b200 import driver, scenes
+    argv = ["--costs", "cvar", "--noises", noise, "--noise_levels", "0.3", "--num_reduced_sets", "5", "--num_obs", str(num_obs),
+            "--num_prime", str(num_prime), "--acc_const_noise", "0.0", "--steer_const_noise", "0.0", "--num_configs", "4",
+            "--root", str(tmp_path), "--variant", variant]
+    args = driver.build_parser().parse_args(argv)
+    written = driver.run_sweep(args, log=lambda *a: None)
+    assert written == [str(tmp_path / f"{noise}_noise" / "noise_30" / f"ts_{num_prime}" / f"cvar_5_samples_{num_obs}_obs.npz")]
+    data = np.load(written[0])
+    ora = O.OracleCEM(5, num_obs, 0.3, num_prime, noise, 0.0, 0.0, variant=variant)
+    init_state, mean, cov, v_des = O.driver_inputs(variant)
+    rows = []
+    for k in range(4):
+        if variant == "dynamic":
+            sc, idx, xt, yt = scenes.dynamic_scene(num_obs, k)
+        else:
+            sc, idx = O.static_episode(num_obs, k)
+            xt, yt, _ = ora.compute_obs_trajectories(*sc)
+        ref = ora.solve("cvar", idx, init_state, mean, cov, xt, yt, v_des)
+        if ref["cost_obs"] <= 1e-5:
+            rows.append((k, ref, sc, xt, yt))
+    assert data["cx"].shape == (len(rows), 11) and data["cx"].dtype == np.float64
+    for r, (k, ref, sc, xt, yt) in enumerate(rows):
+        _eq(data["cx"][r].astype(f32), ref["cx"], f"episode {k} cx"); _eq(data["cy"][r].astype(f32), ref["cy"], f"episode {k} cy")
+        _eq(data["x_obs"][r], np.asarray(sc[0], np.float64), "x_obs"); _eq(data["vx_obs"][r], np.asarray(sc[2], np.float64), "vx_obs")
+        if variant == "dynamic":
+            _eq(data["x_obs_traj"][r].astype(f32), xt, "x_obs_traj"); _eq(data["y_obs_traj"][r].astype(f32), yt, "y_obs_traj")
