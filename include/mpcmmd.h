@@ -107,6 +107,20 @@ int mpcmmd_last_launch_count(mpcmmd_handle h);
  * rollout/risk, select, total}; n_launch[4] = launches per class.  Synchronous. */
 int mpcmmd_profile_solve(mpcmmd_handle h, int cost_kind, int n_ep, float *ms, int *n_launch);
 
+/* Monte-Carlo validation of planned trajectories: the rollout + counting part of `compute_stats`
+ * (synthetic_static_obs/validation.py:134-171, synthetic_dynamic_obs/validation.py:129-165).  The reference draws its noise from
+ * NumPy's legacy MT19937 stream (validation.py:43-84); those draws stay on the host, this entry point takes the PERTURBED controls.
+ * All pointers are HOST pointers, float64 like the reference's NumPy arrays:
+ *   acc, steer (n_ep, n_roll, num_prime); state0 (n_ep,5) = [x, y, vx, vy, psi]; x_obs_traj, y_obs_traj (n_ep, num_obs, num_prime);
+ *   count, count_lane (n_ep,) int32 = max intersections over (obstacle, timestep), lane lb + ub (validation.py:156-169);
+ *   x_roll, y_roll (n_ep, n_roll, num_prime) optional (both NULL to skip).
+ * obs_cost_f32 = 1 evaluates the obstacle cost in float32 (static variant: x_obs_traj is a float32 jax array there), 0 in float64
+ * (dynamic variant).  Synchronous. */
+int mpcmmd_validate_host(int device, int n_ep, int n_roll, int num_prime, int num_obs, int obs_cost_f32, double dt, double wheel_base,
+                         double a_obs, double b_obs, double y_lb, double y_ub, const double *acc, const double *steer,
+                         const double *state0, const double *x_obs_traj, const double *y_obs_traj, int32_t *count,
+                         int32_t *count_lane, double *x_roll, double *y_roll);
+
 /* Measured FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the roofline denominator of the FP32-bound kernels. */
 int mpcmmd_fp32_peak(int device, float *tflops, int *sm_count);
 

@@ -14,6 +14,7 @@
 #include "k_inner_cem.cuh"
 #include "k_inner_cem_warp.cuh"
 #include "k_select.cuh"
+#include "k_validate.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
@@ -523,6 +524,47 @@ extern "C" int mpcmmd_stage_noise(mpcmmd_handle h, int32_t idx_mpc, int32_t iter
     if (z_cem) CK(cudaMemcpy(z_cem, w.zcem + slot * ncem, sizeof(float) * ncem, cudaMemcpyDeviceToDevice));
     if (keys) CK(cudaMemcpy(keys, w.keys + slot * 4, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Monte-Carlo validation (S/validation.py:134-171): host arrays in, counts out.  Not tied to a handle.
+extern "C" int mpcmmd_validate_host(int device, int n_ep, int n_roll, int num_prime, int num_obs, int obs_cost_f32, double dt, double wheel_base,
+                                    double a_obs, double b_obs, double y_lb, double y_ub, const double* acc, const double* steer,
+                                    const double* state0, const double* x_obs_traj, const double* y_obs_traj, int32_t* count,
+                                    int32_t* count_lane, double* x_roll, double* y_roll) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mpcmmd_validate_host: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("mpcmmd_validate_host: bad device index");
+    if (n_ep < 1 || n_roll < 1 || num_prime < 1 || num_prime > MPCMMD_T || num_obs < 1) return fail("mpcmmd_validate_host: bad sizes");
+    if (!acc || !steer || !state0 || !x_obs_traj || !y_obs_traj || !count || !count_lane) return fail("mpcmmd_validate_host: null pointer");
+    if ((x_roll == nullptr) != (y_roll == nullptr)) return fail("mpcmmd_validate_host: x_roll and y_roll must both be given or both be null");
+    const size_t smem = (size_t)(num_obs + 2) * num_prime * sizeof(int);
+    if (smem > 200 * 1024) return fail("mpcmmd_validate_host: (num_obs + 2) * num_prime counters do not fit in shared memory");
+    CK(cudaSetDevice(device));
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_validate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t nc = (size_t)n_ep * n_roll * num_prime, no = (size_t)n_ep * num_obs * num_prime;
+    double *d_acc = nullptr, *d_steer = nullptr, *d_s0 = nullptr, *d_xo = nullptr, *d_yo = nullptr, *d_xr = nullptr, *d_yr = nullptr;
+    int32_t *d_cnt = nullptr, *d_lane = nullptr;
+    int rc = 0;
+    auto body = [&]() -> int {
+        CK(cudaMalloc(&d_acc, nc * 8)); CK(cudaMalloc(&d_steer, nc * 8)); CK(cudaMalloc(&d_s0, (size_t)n_ep * 5 * 8));
+        CK(cudaMalloc(&d_xo, no * 8)); CK(cudaMalloc(&d_yo, no * 8)); CK(cudaMalloc(&d_cnt, (size_t)n_ep * 4)); CK(cudaMalloc(&d_lane, (size_t)n_ep * 4));
+        if (x_roll) { CK(cudaMalloc(&d_xr, nc * 8)); CK(cudaMalloc(&d_yr, nc * 8)); }
+        CK(cudaMemcpy(d_acc, acc, nc * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_steer, steer, nc * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_s0, state0, (size_t)n_ep * 5 * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_xo, x_obs_traj, no * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_yo, y_obs_traj, no * 8, cudaMemcpyHostToDevice));
+        ValCfg c;
+        c.n_roll = n_roll; c.np = num_prime; c.O = num_obs; c.obs_f32 = obs_cost_f32; c.dt = dt; c.wheel_base = wheel_base;
+        c.a2 = a_obs * a_obs; c.b2 = b_obs * b_obs; c.y_lb = y_lb; c.y_ub = y_ub;
+        k_validate<<<n_ep, VAL_THREADS, smem>>>(c, d_acc, d_steer, d_s0, d_xo, d_yo, d_cnt, d_lane, d_xr, d_yr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(count, d_cnt, (size_t)n_ep * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(count_lane, d_lane, (size_t)n_ep * 4, cudaMemcpyDeviceToHost));
+        if (x_roll) { CK(cudaMemcpy(x_roll, d_xr, nc * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(y_roll, d_yr, nc * 8, cudaMemcpyDeviceToHost)); }
+        return 0;
+    };
+    rc = body();
+    cudaFree(d_acc); cudaFree(d_steer); cudaFree(d_s0); cudaFree(d_xo); cudaFree(d_yo); cudaFree(d_cnt); cudaFree(d_lane); cudaFree(d_xr); cudaFree(d_yr);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
