@@ -25,6 +25,7 @@ struct SelArgs {
 };
 
 #define SEL_THREADS 128
+#define SEL_RANK_MAX 1024   // up to this batch size the 64-bit keys are staged in shared memory and ranked by counting
 
 // (risk, res_norm, index) lexicographic "j before i", NaN last in each key
 __device__ __forceinline__ bool sel_before(float rj, float nj, int j, float ri, float ni, int i) {
@@ -55,14 +56,46 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
     __shared__ int s_sel;
     const float* risk = a.risk + (size_t)e * B; const float* res = a.res_norm + (size_t)e * B;
     // position of sample i after the two stable argsorts = rank of (risk, res_norm, index): one 64-bit compare per pair
-    for (int i = tid; i < B; i += SEL_THREADS) skey[i] = ((unsigned long long)sel_key32(risk[i]) << 32) | (unsigned long long)sel_key32(res[i]);
-    __syncthreads();
-    for (int i = tid; i < B; i += SEL_THREADS) {
-        const unsigned long long ki = skey[i];
-        int rank = 0;
+    if (B <= SEL_RANK_MAX) {
+        for (int i = tid; i < B; i += SEL_THREADS) skey[i] = ((unsigned long long)sel_key32(risk[i]) << 32) | (unsigned long long)sel_key32(res[i]);
+        __syncthreads();
+        for (int i = tid; i < B; i += SEL_THREADS) {
+            const unsigned long long ki = skey[i];
+            int rank = 0;
 #pragma unroll 4
-        for (int j = 0; j < B; j++) { const unsigned long long kj = skey[j]; rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0; }
-        if (rank < n20) top[rank] = i;
+            for (int j = 0; j < B; j++) { const unsigned long long kj = skey[j]; rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0; }
+            if (rank < n20) top[rank] = i;
+        }
+    } else {
+        // large batches (scaled configurations): only the first n_el_cost positions are needed, so take them by n_el_cost rounds of
+        // "smallest (key, index) above the previous winner" -- O(n_el_cost * B) instead of the O(B^2) rank count; keys are recomputed
+        // from global memory (L2-resident) instead of being staged in shared memory
+        __shared__ unsigned long long wk[SEL_THREADS / 32];
+        __shared__ int wi[SEL_THREADS / 32];
+        __shared__ unsigned long long last_k; __shared__ int last_i;
+        if (tid == 0) { last_k = 0ull; last_i = -1; }
+        __syncthreads();
+        for (int r = 0; r < n20; r++) {
+            const unsigned long long lk = last_k; const int li = last_i;
+            unsigned long long bk = ~0ull; int bi = 0x7fffffff;
+            for (int j = tid; j < B; j += SEL_THREADS) {
+                const unsigned long long kj = ((unsigned long long)sel_key32(risk[j]) << 32) | (unsigned long long)sel_key32(res[j]);
+                const bool above = (r == 0) || kj > lk || (kj == lk && j > li);
+                if (above && (kj < bk || (kj == bk && j < bi))) { bk = kj; bi = j; }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(FULL, bk, off); const int oi = __shfl_xor_sync(FULL, bi, off);
+                if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+            }
+            if ((tid & 31) == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w2 = 1; w2 < SEL_THREADS / 32; w2++) if (wk[w2] < bk || (wk[w2] == bk && wi[w2] < bi)) { bk = wk[w2]; bi = wi[w2]; }
+                top[r] = bi; last_k = bk; last_i = bi;
+            }
+            __syncthreads();
+        }
     }
     __syncthreads();
     if (tid < n20) cost20[tid] = a.cost_base[(size_t)e * B + top[tid]] + a.w_obs * risk[top[tid]];   // [cem_helper.py:253-261]

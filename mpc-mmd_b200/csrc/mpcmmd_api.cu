@@ -250,6 +250,7 @@ extern "C" int mpcmmd_destroy(mpcmmd_handle h) {
     return 0;
 }
 
+static size_t sel_smem(const DCfg& d) { return d.B <= SEL_RANK_MAX ? 2 * (size_t)d.B * sizeof(float) : 16; }
 static float w_obs_for(const mpcmmd_handle_s* h, int kind) { (void)h; return kind == MPCMMD_COST_SAA ? 1.0e6f : 1.0e3f; }   // cem.py:161-163
 
 static ProjArgs proj_args(mpcmmd_handle_s* h, int n_ep) {
@@ -332,7 +333,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         a.zcem = w.zcem + it * ncem; a.z_stride = (size_t)d.iters * ncem; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma;
         a.res_beta = w.res_beta; a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta;
         a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta; a.o_sel = w.o_sel; a.sel_stride = d.iters;
-        k_select<<<n_ep, SEL_THREADS, 2 * d.B * sizeof(float), s>>>(d, a); mark(3);
+        k_select<<<n_ep, SEL_THREADS, sel_smem(d), s>>>(d, a); mark(3);
     }
     *launches = cnt;
     return 0;
@@ -362,7 +363,6 @@ static int check_solve_args(mpcmmd_handle_s* h, int kind, int n_ep) {
     if (!h) return fail("null handle");
     if (kind < 0 || kind > 3) return fail("mpcmmd_solve: bad cost kind");
     if (n_ep < 1 || n_ep > h->E) return fail("mpcmmd_solve: n_ep outside [1, max_episodes]");
-    if (2 * (size_t)h->d.B * sizeof(float) > 48 * 1024) return fail("mpcmmd_solve: num_batch too large for k_select");
     return 0;
 }
 
@@ -503,7 +503,7 @@ extern "C" int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float* 
     a.zcem = z_cem; a.z_stride = 0; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma; a.res_beta = w.res_beta;
     a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta; a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta;
     a.o_sel = sel; a.sel_stride = 1;
-    k_select<<<1, SEL_THREADS, 2 * d.B * sizeof(float)>>>(d, a);
+    k_select<<<1, SEL_THREADS, sel_smem(d)>>>(d, a);
     CK(cudaDeviceSynchronize());
     return 0;
 }

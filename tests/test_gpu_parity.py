@@ -320,3 +320,31 @@ def test_sweep_driver_writes_reference_schema(mods, tmp_path, variant, num_obs, 
         _eq(data["x_obs"][r], np.asarray(sc[0], np.float64), "x_obs"); _eq(data["vx_obs"][r], np.asarray(sc[2], np.float64), "vx_obs")
         if variant == "dynamic":
             _eq(data["x_obs_traj"][r].astype(f32), xt, "x_obs_traj"); _eq(data["y_obs_traj"][r].astype(f32), yt, "y_obs_traj")
+
+
+def _scaled_episodes(ora, n, nobs):
+    from mpcmmd_b200 import scenes
+    eps = [scenes.scaled_scene(nobs, k) for k in range(n)]
+    tr = [ora.compute_obs_trajectories(*sc) for sc, _ in eps]
+    return [i for _, i in eps], np.stack([t[0] for t in tr]), np.stack([t[1] for t in tr])
+
+
+@pytest.mark.parametrize("cost,noise,B,kw", [
+    ("cvar", "beta", 2048, dict(maxiter_cem=20)),                                                   # large-batch selection path, full depth
+    ("mmd_opt", "gaussian", 1100, dict(maxiter_cem=3, num_samples_cem=40, maxiter_beta_cem=4)),    # just above SEL_RANK_MAX, 27 500 inner chains
+    ("cvar", "gaussian", 16384, dict(maxiter_cem=4)),                                               # BASELINE configs[4] shape: 16k samples x 32 obstacles x 100 steps
+])
+def test_solve_scaled_batch_bit_exact(mods, cost, noise, B, kw):
+    """num_batch far above the reference's 100 (BASELINE configs[4] 'scaled synthetic': 16k CEM samples, 32 obstacles, num_prime 100):
+    k_select takes its O(n_el_cost * B) path, k_project / k_rollouts run B-sized grids.  Bit exact vs the oracle."""
+    cem_impl, O = mods
+    E = 2
+    nobs, npr = (32, 100) if B == 16384 else (12, 60)
+    prob, ora = _pair(mods, (5, nobs, 0.3 if noise == "beta" else 0.1, npr, noise, 0.01, 0.0), max_episodes=E, num_batch=B, **kw)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    idx, xo, yo = _scaled_episodes(ora, E, nobs)
+    got = prob.solve_batch(cost, idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
+    for e in range(E):
+        ref = ora.solve(cost, idx[e], init_state, mean, cov, xo[e], yo[e], v_des)
+        for k in ("cx", "cy", "cost_obs", "cost_lane") + (("beta", "sigma", "res_beta") if cost == "mmd_opt" else ()):
+            _eq(got[k][e], ref[k], f"B={B} {cost} ep{e} {k}")
