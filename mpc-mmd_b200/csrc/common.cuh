@@ -11,7 +11,7 @@
 #define NL 99       // lane rows per side (cem.py:126-134)
 #define NPAR 8      // num_params (cem.py:136)
 #define FULL 0xffffffffu
-#define MPCMMD_MAX_NR_DEV 16   // local-array bound for num_reduced in the small-risk paths
+#define MPCMMD_MAX_NR_DEV 64   // local-array bound for num_reduced in the num_reduced-rollout risk paths (cvar / saa / mmd_random)
 
 struct DCfg {
     int B, np, nr, nm, O, iters, n_el, n_el_cost, noise_kind, S_in, iters_in, n_el_in;

@@ -61,6 +61,31 @@ __device__ __noinline__ float mmd_cost(const DCfg& c, const float* beta, const f
     }
     return c.ker_wt * (s1 - 2.0f * s2);
 }
+// the same value computed by a whole warp (num_reduced <= 64): lane l evaluates the kernel rows i = l, l + 32 as the same ascending-j
+// fma chains, then every lane folds them in ascending i -- bit-identical to mmd_cost, nr^2 / 32 exps per lane instead of nr^2 on one
+__device__ __forceinline__ float mmd_cost_warp(const DCfg& c, const float* beta, const float* cost, float sigma, int lane) {
+    const int nr = c.nr;
+    float tv[2] = {0.0f, 0.0f}, uv[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        if (i < nr) {
+            float t = 0.0f;
+            for (int j = 0; j < nr; j++) t = fmaf(dm::exp_(-fabsf(cost[i] - cost[j]) / sigma), beta[j], t);
+            const float e = dm::exp_(-fabsf(cost[i] - 0.0f) / sigma);
+            float u = 0.0f;
+            for (int j = 0; j < nr; j++) u = fmaf(e, c.beta_del, u);
+            tv[h] = t; uv[h] = u;
+        }
+    }
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int i = 0; i < nr; i++) {
+        const float t = __shfl_sync(FULL, i < 32 ? tv[0] : tv[1], i & 31), u = __shfl_sync(FULL, i < 32 ? uv[0] : uv[1], i & 31);
+        s1 = fmaf(beta[i], t, s1);
+        s2 = fmaf(beta[i], u, s2);
+    }
+    return c.ker_wt * (s1 - 2.0f * s2);
+}
 // jnp.quantile (linear interpolation) + mean of the tail  [costs.py:213-220]
 __device__ __noinline__ float cvar_cost(const DCfg& c, const float* v) {
     const int nr = c.nr;
@@ -97,7 +122,8 @@ struct RollArgs {
     float* feat;             // [n][nm][22]  (mmd_opt only)
     float* stash;            // [persistent CTAs][S][32]  row stash of k_inner_cem_warp
 };
-__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 48); }
+__host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }       // per-rollout cost / lane-lb / lane-ub slots
+__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 4 * roll_tail_floats(nr)); }
 
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
@@ -107,7 +133,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
     const int g0 = blockIdx.x * spb;
     const int ns = min(spb, a.n_samples - g0);                 // samples in this CTA
     if (ns <= 0) return;
-    const int per = 2 * n + 2 * R * np + 48;
+    const int tail = roll_tail_floats(nr), per = 2 * n + 2 * R * np + 4 * tail;
     // ---- perturbed controls  [cem_helper.py:405-443 / 470-508]
 #pragma unroll 1
     for (int i = tid; i < ns * n; i += nt) {
@@ -175,7 +201,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
     for (int ls = warp; ls < ns; ls += nt / 32) {
         const int g = g0 + ls, e = g / a.B;
         const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
-        float* cst = sm + ls * per + 2 * n + 2 * R * np; float* lb = cst + 16; float* ub = lb + 16;
+        float* cst = sm + ls * per + 2 * n + 2 * R * np; float* lb = cst + tail; float* ub = lb + tail; float* bet = ub + tail;
         const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
 #pragma unroll 1
         for (int r = 0; r < nr; r++) {
@@ -192,15 +218,14 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             if (lane == 0) { cst[r] = m; lb[r] = l; ub[r] = u; }
         }
         __syncwarp();
-        if (lane == 0) {
+        if (a.cost_kind == 1) {                           // mmd_random: beta = 1/nr, sigma = 0.01, lane = 0  [cem.py:355-356, 404-424]
+            for (int i = lane; i < nr; i += 32) { bet[i] = c.beta_del; a.beta[(size_t)g * nr + i] = c.beta_del; }
+            __syncwarp();
+            const float risk = mmd_cost_warp(c, bet, cst, c.sigma_random, lane);
+            if (lane == 0) { a.sigma[g] = c.sigma_random; a.risk[g] = risk; a.lane[g] = 0.0f; }
+        } else if (lane == 0) {
             float risk, lanec;
-            if (a.cost_kind == 1) {                       // mmd_random: beta = 1/nr, sigma = 0.01, lane = 0  [cem.py:355-356, 404-424]
-                float beta[MPCMMD_MAX_NR_DEV];
-                for (int i = 0; i < nr; i++) { beta[i] = c.beta_del; a.beta[(size_t)g * nr + i] = c.beta_del; }
-                a.sigma[g] = c.sigma_random;
-                risk = mmd_cost(c, beta, cst, c.sigma_random);
-                lanec = 0.0f;
-            } else if (a.cost_kind == 2) {                // cvar  [costs.py:206-221, 137-158]
+            if (a.cost_kind == 2) {                       // cvar  [costs.py:206-221, 137-158]
                 risk = cvar_cost(c, cst);
                 lanec = cvar_cost(c, lb) + cvar_cost(c, ub);
             } else {                                      // saa  [costs.py:223-234, 160-171]
@@ -232,7 +257,7 @@ __host__ __device__ inline OptLayout opt_layout(int nr, int np, int S, int ne) {
     L.ldc = al4(d);
     int q = 0;
     L.F = q; q += al4(nm * 2 * NV); L.D = q; q += al4(nm * nm); L.small = q; q += 64;
-    L.red = q; q += al4(3 * MPCMMD_MAX_NR_DEV * (RISKO_THREADS / 32));
+    L.red = q; q += al4(3 * 16 * (RISKO_THREADS / 32));
     L.th = q; q += al4(S * d); L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S * nr);
     L.key64 = q; q += al4(2 * S); L.perm = q; q += al4(S); L.C = q; q += al4(d * L.ldc); L.rd = q; q += al4(d); L.mean = q; q += al4(d);
     L.eth = q; q += al4(ne * d); L.xc = q; q += al4(ne * d); L.ecost = q; q += al4(ne); L.ebetas = q; q += al4(ne * nr); L.eidxs = q; q += al4(ne * nr);

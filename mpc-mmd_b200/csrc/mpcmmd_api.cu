@@ -125,7 +125,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     if (B < cfg->ellite_num_cost || cfg->ellite_num_cost > 32 || cfg->ellite_num > 8 || cfg->ellite_num > cfg->ellite_num_cost)
         return fail("mpcmmd_create: need ellite_num <= 8, ellite_num <= ellite_num_cost <= min(32, num_batch)");
     if (np < 2 || np > MPCMMD_T) return fail("mpcmmd_create: num_prime must be in [2,100]");
-    if (nr < 2 || nr > MPCMMD_MAX_NR) return fail("mpcmmd_create: num_reduced must be in [2,10]");
+    if (nr < 2 || nr > MPCMMD_MAX_NR_DEV) return fail("mpcmmd_create: num_reduced must be in [2,64] (mmd_opt: one of 2,3,4,5,6,8,10)");
     if (cfg->num_obs < 1 || E < 1) return fail("mpcmmd_create: num_obs and max_episodes must be >= 1");
     if (cfg->num_samples_cem > RISKO_THREADS * 8 || cfg->num_ellite_beta < 2 || cfg->num_ellite_beta >= cfg->num_samples_cem)
         return fail("mpcmmd_create: bad inner-CEM sizes");
@@ -209,7 +209,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     // opt-in shared memory sizes
     if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
     {
-        size_t rs = roll_smem(d, MPCMMD_COST_MMD_OPT); const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
+        size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(d, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
         if (rs > 48 * 1024 && cudaFuncSetAttribute(k_rollouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
     }
@@ -268,6 +268,7 @@ static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s)
 // mother rollouts / features scratch of the mmd_opt path, allocated on first use ([E*B][nm][np] x2 and [E*B][nm][22])
 static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (h->xroll) return 0;
+    if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10 (larger reduced sets: cvar / saa / mmd_random only)");
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
     if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;

@@ -348,3 +348,24 @@ def test_solve_scaled_batch_bit_exact(mods, cost, noise, B, kw):
         ref = ora.solve(cost, idx[e], init_state, mean, cov, xo[e], yo[e], v_des)
         for k in ("cx", "cy", "cost_obs", "cost_lane") + (("beta", "sigma", "res_beta") if cost == "mmd_opt" else ()):
             _eq(got[k][e], ref[k], f"B={B} {cost} ep{e} {k}")
+
+
+@pytest.mark.parametrize("nr,npr", [(10, 20), (20, 60), (40, 100), (40, 20)])
+@pytest.mark.parametrize("cost", ["mmd_random", "cvar"])
+def test_stage_risk_large_reduced_sets(mods, cost, nr, npr):
+    """BASELINE configs[3]: the MMD / CVaR risk stage over num_reduced in {5,10,20,40} x num_prime in {20..100} (num_reduced rollouts per
+    sample, warp-parallel Laplace-kernel MMD); bit exact vs the oracle on 64 samples"""
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (nr, 6, 0.1, npr, "gaussian", 0.02, 0.01), max_episodes=1)
+    rng = np.random.default_rng(nr * 1000 + npr)
+    acc, steer = _controls(ora, rng, 64)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(77, 2)
+    from mpcmmd_b200 import scenes
+    sc, _ = scenes.static_scene(6, 3)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    got = prob.stage_risk(cost, acc, steer, st0, noise_t, xo, yo)
+    for i in range(64):
+        ref = ora.risk(cost, acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane"):
+            _eq(got[k][i], ref[k], f"{cost} nr={nr} np={npr} sample {i} {k}")
