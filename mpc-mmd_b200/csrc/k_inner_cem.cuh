@@ -336,6 +336,58 @@ __device__ __forceinline__ void icf_chol(float* __restrict__ C, int ldc, int lan
     __syncwarp();
 }
 
+// Latency variant (used when the whole launch is a single wave of CTAs, e.g. one episode = 100 chains): +2000 SASS instructions, which costs
+// ~10 % throughput on full grids through the instruction cache (measured 208.6 -> 229.8 ms per 200-episode solve) but shortens the pivot
+// chain (mmd_opt p50 latency at batch 1: 8.87 -> 7.54 ms).
+// Cholesky of the d x d covariance by ONE warp, right-looking: lane i holds row i of the lower triangle IN REGISTERS; step j turns column j
+// into row j of LT (LT[j][q] = L[q][j] for q >= j, zeros for q < j; LT overwrites C in place -- every lane has its row in registers before
+// the first store) and subtracts l_ij * LT[j][q] from a[q], q > j.  Entry (i,q) therefore accumulates fma(-L_ik, L_qk, .) for k ascending:
+// the contract's order.  Fully unrolled: the pivot chain (shfl -> sqrt -> 1/x -> store -> broadcast loads) is the critical path of the
+// whole CTA -- 2 of its 3 warps wait at the barrier behind it (profiles/r01_v8_summary.md: 28 % of all stall samples) -- and the rolled
+// shared-memory version spent 93 warp instructions per pivot against ~35 here.  Entries q > i of a lane hold unused values.
+template <int d>
+__device__ __forceinline__ void icf_chol_unrolled(float* __restrict__ C, int ldc, int lane) {
+    constexpr int NG = (d + 3) / 4;
+    float* LT = C;
+    float a[4 * NG];
+    {
+        const float* rowp = C + (lane < d ? lane : d - 1) * ldc;
+#pragma unroll
+        for (int g4 = 0; g4 < NG; g4++) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + 4 * g4);
+            a[4 * g4] = v.x; a[4 * g4 + 1] = v.y; a[4 * g4 + 2] = v.z; a[4 * g4 + 3] = v.w;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < d; j++) {
+        const float ajj = __shfl_sync(FULL, a[j], j);
+        const float dd = sqrtf(ajj);
+        const float rdj = 1.0f / dd;
+        const float lij = lane == j ? dd : a[j] * rdj;
+        if (lane < d) LT[j * ldc + lane] = lane < j ? 0.0f : lij;
+        if (j + 1 < d) {
+            __syncwarp();
+            const pk::f2 nl = pk::dup(-lij);
+            const float* lrow = LT + j * ldc;
+#pragma unroll
+            for (int g4 = (j + 1) / 4; g4 < NG; g4++) {
+                const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * g4);
+                // columns q <= j of the first group are final already (never read again): only q > j is updated
+                if (4 * g4 + 1 > j) {
+                    if (4 * g4 > j) pk::unpack(pk::fma2(nl, pk::pack(l.x, l.y), pk::pack(a[4 * g4], a[4 * g4 + 1])), a[4 * g4], a[4 * g4 + 1]);
+                    else a[4 * g4 + 1] = fmaf(-lij, l.y, a[4 * g4 + 1]);
+                }
+                if (4 * g4 + 3 > j) {
+                    if (4 * g4 + 2 > j) pk::unpack(pk::fma2(nl, pk::pack(l.z, l.w), pk::pack(a[4 * g4 + 2], a[4 * g4 + 3])), a[4 * g4 + 2], a[4 * g4 + 3]);
+                    else a[4 * g4 + 3] = fmaf(-lij, l.w, a[4 * g4 + 3]);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // one covariance task: C[r][4*q4 .. 4*q4+3] = (sum_el xc[el][r] * xc[el][q]) / (ne - 1) (+ 0.05 on the diagonal), el ascending  [compute_beta.py:61]
 __device__ __forceinline__ void icf_cov_task(const float* __restrict__ xc, float* __restrict__ C, int ldc, int ne, int r, int q4) {
     const float nm1 = (float)(ne - 1);
@@ -407,7 +459,7 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
     }
 }
 
-template <int NR>
+template <int NR, bool LAT>
 __global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
     const RiskArgs& a = ra.r;
@@ -417,7 +469,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollA
     static_assert(d <= 32, "one covariance row per lane");
     constexpr int NPAIR = (d + 1) / 2;               // packed column pairs of a covariance / Cholesky row
     const int tid = threadIdx.x, nt = ICF_THREADS, warp = tid >> 5, lane = tid & 31;
-    const int e = g / a.B, np = c.np, S = c.S_in, ne = c.n_el_in;
+    const int S = c.S_in, ne = c.n_el_in;
     const FastLayout L = fast_layout(NR, S, ne);
     const int ldt = L.ldt, ldc = L.ldc;
     float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = sm + L.betas; int* idxs = (int*)(sm + L.idxs);
@@ -506,7 +558,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollA
         // -- Cholesky by warp 0, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j into row j of
         //    LT (LT[j][q] = L[q][j], q >= j; zeros for q < j) and subtracts l_ij * LT[j][q] from A[i][q], j < q <= i.  Entry (i,q)
         //    therefore accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.  Rolled on purpose (instruction cache).
-        if (warp == 0) icf_chol<d>(C, ldc, lane);
+        if (warp == 0) { if constexpr (LAT) icf_chol_unrolled<d>(C, ldc, lane); else icf_chol<d>(C, ldc, lane); }
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
         //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in
@@ -546,38 +598,40 @@ __global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollA
         // the next iteration's first barrier (after the evaluation) orders these reads against later writes of perm / th
     }
     __syncthreads();
-    // ---- risk of the chosen reduced set (its rollouts come back from global memory)  [costs.py:173-186, 121-135]
-    const int* ridx = (const int*)small + 16;
+    // ---- hand the chosen reduced set to k_opt_risk (a separate kernel: the ~2000 SASS instructions of the risk evaluation would otherwise
+    //      share the instruction cache with the 20-iteration loop of the other resident chains)
+    if (tid < NR) { a.beta[(size_t)g * NR + tid] = small[tid]; ra.ridx[(size_t)g * NR + tid] = ((const int*)small)[16 + tid]; }
+    if (tid == 0) a.sigma[g] = small[48];
+}
+
+// risk of the reduced set k_inner_cem_fast chose (its rollouts come back from global memory): one warp per sample  [costs.py:173-186, 121-135]
+#define OPT_RISK_WARPS 4
+__global__ void __launch_bounds__(OPT_RISK_WARPS * 32) k_opt_risk(DCfg c, RollArgs ra) {
+    const RiskArgs& a = ra.r;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * OPT_RISK_WARPS + warp;
+    if (g >= a.n_samples) return;
+    const int e = g / a.B, np = c.np, nr = c.nr, nm = c.nm;
+    const int* ridx = ra.ridx + (size_t)g * nr;
     const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
     const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    constexpr int NW = ICF_THREADS / 32;
-    float* red = sm + L.red;
+    float cs[MPCMMD_MAX_NR], lbv[MPCMMD_MAX_NR], ubv[MPCMMD_MAX_NR], beta[MPCMMD_MAX_NR];
 #pragma unroll 1
-    for (int r = 0; r < NR; r++) {
+    for (int r = 0; r < nr; r++) {
         const float* xred = xg + ridx[r] * np; const float* yred = yg + ridx[r] * np;
         float m = 0.0f, l = 0.0f, u = 0.0f;
-        for (int i = tid; i < c.O * np; i += nt) {
+        for (int i = lane; i < c.O * np; i += 32) {
             const int o = i / np, t = i % np;
             m = dm::nmax_(m, fbar(c, xred[t], yred[t], xo[o * T_ + t], yo[o * T_ + t]));
         }
-        for (int t = tid; t < np; t += nt) {
+        for (int t = lane; t < np; t += 32) {
             l = dm::nmax_(l, dm::max0_(-yred[t] + c.y_lb));
             u = dm::nmax_(u, dm::max0_(yred[t] - c.y_ub));
         }
-        m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
-        if (lane == 0) { red[(r * 3 + 0) * NW + warp] = m; red[(r * 3 + 1) * NW + warp] = l; red[(r * 3 + 2) * NW + warp] = u; }
+        cs[r] = warp_nmax(m); lbv[r] = warp_nmax(l); ubv[r] = warp_nmax(u); beta[r] = a.beta[(size_t)g * nr + r];
     }
-    __syncthreads();
-    if (tid == 0) {
-        float cs[NR], lbv[NR], ubv[NR], beta[NR];
-        for (int r = 0; r < NR; r++) {
-            float m = red[(r * 3 + 0) * NW], l = red[(r * 3 + 1) * NW], u = red[(r * 3 + 2) * NW];
-            for (int wv = 1; wv < NW; wv++) { m = dm::nmax_(m, red[(r * 3 + 0) * NW + wv]); l = dm::nmax_(l, red[(r * 3 + 1) * NW + wv]); u = dm::nmax_(u, red[(r * 3 + 2) * NW + wv]); }
-            cs[r] = m; lbv[r] = l; ubv[r] = u; beta[r] = small[r];
-            a.beta[(size_t)g * NR + r] = small[r];
-        }
-        const float sigma = small[48];
-        a.sigma[g] = sigma;
+    if (lane == 0) {
+        const float sigma = a.sigma[g];
         a.risk[g] = mmd_cost(c, beta, cs, sigma);
         a.lane[g] = mmd_cost(c, beta, lbv, sigma) + mmd_cost(c, beta, ubv, sigma);
     }

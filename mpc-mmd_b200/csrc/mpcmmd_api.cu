@@ -30,12 +30,15 @@ struct mpcmmd_handle_s {
     DWork w;
     float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
     float *xroll = nullptr, *yroll = nullptr, *feat = nullptr;     // mmd_opt scratch (ensure_opt_scratch)
+    int* ridx = nullptr;       // [E*B][nr] reduced sets (k_inner_cem_fast -> k_opt_risk)
     float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
     int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
+    int sm_count = 148;
     int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic (MPCMMD_INNER_CEM=auto|warp|cta|generic)
     int E = 0;
     std::vector<void*> allocs;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    std::map<std::pair<int, int>, int> graph_launches;
     int last_launches = 0;
     cudaStream_t own_stream = nullptr;
 };
@@ -90,13 +93,16 @@ static size_t roll_smem_for(const DCfg& d, int kind, int spb) {
 static size_t roll_smem(const DCfg& d, int kind) { return roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30)); }
 
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3 };
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4 };
 static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_WARP) switch (d.nr) {
         case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
     }
     if (kind == INNER_CTA) switch (d.nr) {
-        case 2: return k_inner_cem_fast<2>; case 3: return k_inner_cem_fast<3>; case 4: return k_inner_cem_fast<4>; case 5: return k_inner_cem_fast<5>;
+        case 2: return k_inner_cem_fast<2, false>; case 3: return k_inner_cem_fast<3, false>; case 4: return k_inner_cem_fast<4, false>; case 5: return k_inner_cem_fast<5, false>;
+    }
+    if (kind == INNER_CTA_LAT) switch (d.nr) {
+        case 2: return k_inner_cem_fast<2, true>; case 3: return k_inner_cem_fast<3, true>; case 4: return k_inner_cem_fast<4, true>; case 5: return k_inner_cem_fast<5, true>;
     }
     switch (d.nr) {
         case 2: return k_inner_cem<2>;
@@ -111,7 +117,7 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
 }
 static size_t inner_cem_smem_kind(const DCfg& d, int kind) {
     if (kind == INNER_WARP) return (size_t)warp_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
-    if (kind == INNER_CTA) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    if (kind == INNER_CTA || kind == INNER_CTA_LAT) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
     return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
 }
 
@@ -215,9 +221,11 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     }
     {
         const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
-        h->inner_mode = !mode ? 0 : !strcmp(mode, "warp") ? INNER_WARP : !strcmp(mode, "cta") ? INNER_CTA : !strcmp(mode, "generic") ? INNER_GENERIC : 0;
-        if (!inner_cem_is_fast(d) && (h->inner_mode == INNER_WARP || h->inner_mode == INNER_CTA)) h->inner_mode = INNER_GENERIC;
-        for (int kind = INNER_WARP; kind <= INNER_GENERIC; kind++) {
+        h->inner_mode = !mode ? 0 : !strcmp(mode, "warp") ? INNER_WARP : !strcmp(mode, "cta") ? INNER_CTA : !strcmp(mode, "generic") ? INNER_GENERIC :
+                        !strcmp(mode, "lat") ? INNER_CTA_LAT : 0;
+        if (!inner_cem_is_fast(d) && h->inner_mode != 0) h->inner_mode = INNER_GENERIC;
+        cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+        for (int kind = INNER_WARP; kind <= INNER_CTA_LAT; kind++) {
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
             inner_cem_fn f = inner_cem_kernel(d, kind);
             if (!f) continue;
@@ -271,6 +279,7 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10 (larger reduced sets: cvar / saa / mmd_random only)");
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
     if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
+    if (dalloc(h, &h->ridx, EB * d.nr)) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
     return 0;
 }
@@ -280,14 +289,15 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr;
+    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx;
     inner_cem_fn f = nullptr;
     int kind = INNER_GENERIC;
     if (opt) {
         // default: one 3-warp CTA per chain (k_inner_cem_fast).  The warp-per-chain persistent kernel is kept as an opt-in
         // (MPCMMD_INNER_CEM=warp): measured 233 ms vs 209 ms per 200-episode mmd_opt solve on B200 (profiles/r01_v7_summary.md) --
         // 19 independent instruction streams per SM thrash the 32 KB instruction cache.
-        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : INNER_CTA;
+        // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the unrolled-Cholesky build
+        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 9 * h->sm_count ? INNER_CTA_LAT : INNER_CTA);
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
         f = inner_cem_kernel(d, kind);
         if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
@@ -299,8 +309,12 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
         if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
-        else f<<<r.n_samples, kind == INNER_CTA ? ICF_THREADS : RISKO_THREADS, sm, s>>>(d, ra);
+        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : RISKO_THREADS, sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
+        if (kind == INNER_CTA || kind == INNER_CTA_LAT) {
+            k_opt_risk<<<(r.n_samples + OPT_RISK_WARPS - 1) / OPT_RISK_WARPS, OPT_RISK_WARPS * 32, 0, s>>>(d, ra);
+            if (n_launch) *n_launch = 3;
+        }
     }
     return 0;
 }
@@ -327,7 +341,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
         int nl = 0;
         if (launch_risk(h, r, s, &nl)) return -1;
-        mark(2); if (nl == 2) cnt++;
+        mark(2); cnt += nl - 1;
         SelArgs a;
         a.n_ep = n_ep; a.B = d.B; a.it = it; a.nr = d.nr; a.iters_in = d.iters_in; a.w_obs = w_obs_for(h, kind);
         a.res_norm = w.res_norm; a.risk = w.risk; a.lane = w.lane; a.cost_base = w.cost_base; a.params = w.params; a.mean = w.mean; a.cov = w.cov;
@@ -343,7 +357,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
 static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
     auto key = std::make_pair(kind, n_ep);
     auto it = h->graphs.find(key);
-    if (it != h->graphs.end()) { *out = it->second; h->last_launches = 3 + (kind == MPCMMD_COST_MMD_OPT ? 4 : 3) * h->d.iters; return 0; }
+    if (it != h->graphs.end()) { *out = it->second; h->last_launches = h->graph_launches[key]; return 0; }
     cudaGraph_t g;
     int launches = 0;
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
@@ -355,6 +369,7 @@ static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* ou
     CK(cudaGraphInstantiate(&ge, g, 0));
     cudaGraphDestroy(g);
     h->graphs[key] = ge;
+    h->graph_launches[key] = launches;
     h->last_launches = launches;
     *out = ge;
     return 0;
