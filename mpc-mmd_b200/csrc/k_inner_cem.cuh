@@ -62,7 +62,8 @@ __host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
     int q = 0;
     L.D = q; q += al4(nm * nm);
     L.th = q; q += al4(S * L.ldt > nm * 2 * NV ? S * L.ldt : nm * 2 * NV);      // new rows; aliased by the mother features while D is built
-    L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S);      // idxs: num_reduced 5-bit indices packed per row
+    L.cost = q; q += al4(S); L.betas = q; L.idxs = q;      // the per-row beta / packed-index records live in a global scratch (L2): only <= ne of S rows are read back
+                                                           // per iteration, and the 2.4 KB they took in shared memory is what separates 9 from 10 chains per SM
     L.eth = q; q += 2 * al4(ne * L.ldt); L.ecost = q; q += 2 * al4(ne); L.ebetas = q; q += 2 * al4(ne * nr); L.eidxs = q; q += 2 * al4(ne);
     L.perm = q; q += al4(ne);
     L.xc = q; q += ICF_MAX_NE * L.ldc;       // centered elites, row el, 16-byte aligned rows
@@ -460,7 +461,7 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
 }
 
 template <int NR, bool LAT>
-__global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 9) k_inner_cem_fast(DCfg c, RollA
     const int S = c.S_in, ne = c.n_el_in;
     const FastLayout L = fast_layout(NR, S, ne);
     const int ldt = L.ldt, ldc = L.ldc;
-    float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = sm + L.betas; int* idxs = (int*)(sm + L.idxs);
+    float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = ra.bscratch + (size_t)g * S * (NR + 1); int* idxs = (int*)(betas + S * NR);
     int* perm = (int*)(sm + L.perm); float* xc = sm + L.xc; float* C = sm + L.C; float* LT = C; float* mean = sm + L.mean;
     float* small = sm + L.small;
     const int eth_sz = al4(ne * ldt), ecost_sz = al4(ne), eb_sz = al4(ne * NR), ei_sz = al4(ne);

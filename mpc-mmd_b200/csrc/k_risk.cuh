@@ -122,6 +122,7 @@ struct RollArgs {
     float* feat;             // [n][nm][22]  (mmd_opt only)
     float* stash;            // [persistent CTAs][S][32]  row stash of k_inner_cem_warp
     int* ridx;               // [n][nr]  reduced set chosen by k_inner_cem_fast, read by k_opt_risk
+    float* bscratch;         // [n][S][nr + 1]  per-row beta vectors and packed reduced-set indices of k_inner_cem_fast's current iteration
 };
 __host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }       // per-rollout cost / lane-lb / lane-ub slots
 __host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 4 * roll_tail_floats(nr)); }

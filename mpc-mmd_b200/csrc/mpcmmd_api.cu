@@ -31,6 +31,7 @@ struct mpcmmd_handle_s {
     float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
     float *xroll = nullptr, *yroll = nullptr, *feat = nullptr;     // mmd_opt scratch (ensure_opt_scratch)
     int* ridx = nullptr;       // [E*B][nr] reduced sets (k_inner_cem_fast -> k_opt_risk)
+    float* bscratch = nullptr; // [E*B][S][nr+1] row records of k_inner_cem_fast
     float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
     int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
     int sm_count = 148;
@@ -232,8 +233,8 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
             const size_t sm = inner_cem_smem_kind(d, kind);
             if (sm > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
+            if (kind != INNER_GENERIC) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (kind == INNER_WARP) {
-                cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 int per_sm = 0, sms = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -280,6 +281,7 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
     if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
     if (dalloc(h, &h->ridx, EB * d.nr)) return -1;
+    if (inner_cem_is_fast(d) && dalloc(h, &h->bscratch, EB * d.S_in * (d.nr + 1))) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
     return 0;
 }
@@ -289,7 +291,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx;
+    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch;
     inner_cem_fn f = nullptr;
     int kind = INNER_GENERIC;
     if (opt) {
