@@ -30,9 +30,35 @@ for p in (ROOT, os.path.join(ROOT, "mpc-mmd_b200")):
 WORK = dict(num_reduced=5, num_obs=4, noise_level=0.3, num_prime=50, noise="beta", acc_const_noise=0.0, steer_const_noise=0.0)
 COSTS = ("cvar", "mmd_opt")
 EPISODES = 200
+VARIANT = "static"
+CEM_KW = {}
 WORKLOAD_NAME = ("configs[1]: synthetic_static_obs, cvar + mmd_opt, beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5, "
                  "200 episodes per GPU (400 solves/step/GPU)")
 METRIC = "MPC solves/sec"
+
+# The default (and the driver's) workload is configs[1].  The other BASELINE configs are parity-test cases (tests/); `--workload` lets
+# them be timed with the same harness for the numbers quoted in DESIGN.md / profiles/ -- those lines are not the headline.
+WORKLOADS = {
+    "cfg2": None,
+    "cfg3": dict(work=dict(num_reduced=5, num_obs=6, noise_level=0.1, num_prime=60, noise="gaussian", acc_const_noise=0.0, steer_const_noise=0.0),
+                 costs=("mmd_opt",), episodes=200, variant="dynamic", kw={},
+                 name="configs[2]: synthetic_dynamic_obs, mmd_opt, gaussian noise 0.1, num_obs 6, num_prime 60, num_reduced 5, 200 episodes per GPU"),
+    "cfg3b": dict(work=dict(num_reduced=5, num_obs=6, noise_level=0.3, num_prime=60, noise="beta", acc_const_noise=0.0, steer_const_noise=0.0),
+                  costs=("mmd_opt",), episodes=200, variant="dynamic", kw={},
+                  name="configs[2]: synthetic_dynamic_obs, mmd_opt, beta noise 0.3, num_obs 6, num_prime 60, num_reduced 5, 200 episodes per GPU"),
+    "cfg5": dict(work=dict(num_reduced=5, num_obs=32, noise_level=0.1, num_prime=100, noise="gaussian", acc_const_noise=0.0, steer_const_noise=0.0),
+                 costs=("cvar",), episodes=25, variant="static", kw=dict(num_batch=16384),
+                 name="configs[4] (scaled synthetic): cvar, 16384 CEM samples x 32 obstacles x num_prime 100, 25 episodes per GPU per step "
+                      "(the 200-per-GPU sweep is 8 such steps)"),
+}
+
+
+def select_workload(name):
+    global WORK, COSTS, EPISODES, VARIANT, CEM_KW, WORKLOAD_NAME
+    w = WORKLOADS[name]
+    if w is None:
+        return
+    WORK, COSTS, EPISODES, VARIANT, CEM_KW, WORKLOAD_NAME = w["work"], w["costs"], w["episodes"], w["variant"], w["kw"], w["name"]
 
 
 def cem_args():
@@ -44,11 +70,15 @@ def cem_args():
 # CPU arm: the oracle port (the reference itself needs jax==0.3.23, absent from this image), naive formulation
 def cpu_arm_step(ora, O, episodes):
     """solve `episodes` with both costs on the host; returns number of solves"""
-    init_state, mean, cov, v_des = O.driver_inputs("static")
+    from mpcmmd_b200 import scenes            # host-only scene generators (NumPy), shared with the CUDA arm so both solve the same inputs
+    init_state, mean, cov, v_des = scenes.driver_inputs(VARIANT)
     n = 0
     for k in episodes:
-        sc, idx = O.static_episode(WORK["num_obs"], k)
-        xo, yo, _ = ora.compute_obs_trajectories(*sc)
+        if VARIANT == "dynamic":
+            _, idx, xo, yo = scenes.dynamic_scene(WORK["num_obs"], k)
+        else:
+            sc, idx = scenes.static_scene(WORK["num_obs"], k) if WORK["num_obs"] <= 9 else scenes.scaled_scene(WORK["num_obs"], k)
+            xo, yo, _ = ora.compute_obs_trajectories(*sc)
         for cost in COSTS:
             ora.solve(cost, idx, init_state, mean, cov, xo, yo, v_des)
             n += 1
@@ -59,7 +89,7 @@ def make_cpu_arm():
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     O.set_threads(cores)
-    ora = O.OracleCEM(*cem_args(), variant="static", naive=True)
+    ora = O.OracleCEM(*cem_args(), variant=VARIANT, naive=True, **CEM_KW)
     return ora, O, cores
 
 
@@ -68,7 +98,7 @@ def run_reference(args, emit):
     if rank != 0:
         return 0
     ora, O, cores = make_cpu_arm()
-    sample = "episode 0 of the sweep, cvar + mmd_opt (2 solves per step), oracle port in the reference's naive formulation, %d host threads" % cores
+    sample = "episode 0 of the sweep, %s (%d solves per step), oracle port in the reference's naive formulation, %d host threads" % (" + ".join(COSTS), len(COSTS), cores)
     for _ in range(args.warmup):
         cpu_arm_step(ora, O, [0])
     t0 = time.perf_counter()
@@ -79,7 +109,7 @@ def run_reference(args, emit):
     val = n / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample_per_step": "1 episode x 2 costs"},
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample_per_step": "1 episode x %d costs" % len(COSTS)},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -136,7 +166,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args, emit)
 
@@ -160,15 +192,16 @@ def main():
     from mpcmmd_b200 import CEM, cem_impl, scenes
     W, K, E = max(args.warmup, 3), args.steps, EPISODES
 
-    prob = CEM(*cem_args(), variant="static", max_episodes=E, device=local)
+    prob = CEM(*cem_args(), variant=VARIANT, max_episodes=E, device=local, **CEM_KW)
     eps = list(range(rank * E, rank * E + E))
-    host = scenes.static_batch(prob, eps)
+    host = scenes.static_batch(prob, eps, VARIANT)
     keys = ("idx_mpc", "init_state", "mean_param", "cov_param", "x_obs_traj", "y_obs_traj", "v_des")
     dev_in = {k: torch.as_tensor(host[k], device=dev) for k in keys}
     pinned = {k: torch.as_tensor(host[k]).pin_memory() for k in keys}
     pinned_np = {k: pinned[k].numpy() for k in keys}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
     thresholds = {"cvar": 1e-5, "mmd_opt": -prob.ker_wt + 1.0}                    # main_mpc.py:88-97
+    HEAVY = COSTS[-1]                                                             # the cost whose risk stage the roofline describes
 
     def record(out, cost):
         """26-float per-episode record [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] gathered over ranks"""
@@ -238,31 +271,38 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = solves_per_step * K / float(e2e_t.item())
     h2d = len(COSTS) * sum(int(pinned_np[k].nbytes) for k in keys)
-    d2h = len(COSTS) * sum(int(v.nbytes) for v in outs["mmd_opt"].values())
+    d2h = len(COSTS) * sum(int(v.nbytes) for v in outs[HEAVY].values())
     same = all(np.array_equal(outs[c]["cx"], recs[c][rank * E:(rank + 1) * E, 4:15].cpu().numpy()) for c in COSTS)
 
     # ---- roofline of the dominant kernel (k_risk_opt: rollouts + reduced-set CEM + risk), launch-by-launch CUDA events
-    prob.solve_batch_device("mmd_opt", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
-    prof = prob.profile_solve("mmd_opt", E)
+    prob.solve_batch_device(HEAVY, *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+    prof = prob.profile_solve(HEAVY, E)
     prof_cvar = None
-    prob.solve_batch_device("cvar", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
-    prof_cvar = prob.profile_solve("cvar", E)
-    fl = scenes.flops_per_sample("mmd_opt", WORK["num_reduced"], WORK["num_prime"], WORK["num_obs"])
+    if "cvar" in COSTS and HEAVY != "cvar":
+        prob.solve_batch_device("cvar", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+        prof_cvar = prob.profile_solve("cvar", E)
+    fl = scenes.flops_per_sample(HEAVY, WORK["num_reduced"], WORK["num_prime"], WORK["num_obs"])
     flops_per_launch = fl["risk"] * prob.num_batch * E
     avg_launch_s = prof["ms"]["risk"] * 1e-3 / prof["launches"]["risk"]
     peak_tf, sm_count = cem_impl.fp32_peak(local)
     achieved = flops_per_launch / avg_launch_s / 1e12
-    roofline = {"bound": "fp32", "kernel": "k_risk_opt<5> (rollouts + reduced-set inner CEM + MMD risk)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+    # dram bytes per risk-stage launch from the committed ncu --set full captures (profiles/r01_v8_summary.md): k_inner_cem_fast 123 + 69 MB,
+    # k_rollouts 19 + 221 MB at the cfg2 shape; null for the other workloads (not captured)
+    traffic = 432.0e6 if (args.workload == "cfg2") else None
+    roofline = {"bound": "fp32", "kernel": ("k_rollouts + k_inner_cem_fast<5> + k_opt_risk (mother rollouts, reduced-set inner CEM, MMD risk)" if HEAVY == "mmd_opt"
+                                            else "k_rollouts (noisy rollouts + %s risk)" % HEAVY), "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "peak_source": "measured in this run: register-resident FP32 fma micro-kernel (MEASURED_PEAKS.json has no FP32 figure)",
                 "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "sm_count": sm_count,
-                "kernel_share_of_mmd_opt_solve": prof["ms"]["risk"] / prof["ms"]["total"],
-                "mmd_opt_ms_by_kernel": prof["ms"], "cvar_ms_by_kernel": prof_cvar["ms"]}
+                "kernel_share_of_%s_solve" % HEAVY: prof["ms"]["risk"] / prof["ms"]["total"],
+                "%s_ms_by_kernel" % HEAVY: prof["ms"]}
+    if prof_cvar:
+        roofline["cvar_ms_by_kernel"] = prof_cvar["ms"]
 
     # ---- per-solve latency at batch = 1 (BASELINE.json's second headline)
     lat = {}
     if rank == 0:
-        p1 = CEM(*cem_args(), variant="static", max_episodes=1, device=local)
+        p1 = CEM(*cem_args(), variant=VARIANT, max_episodes=1, device=local, **CEM_KW)
         one = {k: dev_in[k][:1].contiguous() for k in keys}
         for cost in COSTS:
             for _ in range(5):
@@ -285,7 +325,7 @@ def main():
         n = cpu_arm_step(ora, O, [0, 1])
         dt = time.perf_counter() - t0
         cpu = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": "episodes 0-1 of the sweep x {cvar, mmd_opt} = 4 solves in %.1f s; oracle port (C, reference's naive formulation), %d host threads" % (dt, cores)}
+               "sample": "episodes 0-1 of the sweep x {%s} = %d solves in %.1f s; oracle port (C, reference's naive formulation), %d host threads" % (", ".join(COSTS), n, dt, cores)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,

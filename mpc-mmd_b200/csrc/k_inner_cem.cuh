@@ -621,13 +621,11 @@ __global__ void __launch_bounds__(OPT_RISK_WARPS * 32) k_opt_risk(DCfg c, RollAr
     for (int r = 0; r < nr; r++) {
         const float* xred = xg + ridx[r] * np; const float* yred = yg + ridx[r] * np;
         float m = 0.0f, l = 0.0f, u = 0.0f;
-        for (int i = lane; i < c.O * np; i += 32) {
-            const int o = i / np, t = i % np;
-            m = dm::nmax_(m, fbar(c, xred[t], yred[t], xo[o * T_ + t], yo[o * T_ + t]));
-        }
         for (int t = lane; t < np; t += 32) {
-            l = dm::nmax_(l, dm::max0_(-yred[t] + c.y_lb));
-            u = dm::nmax_(u, dm::max0_(yred[t] - c.y_ub));
+            const float x = xred[t], y = yred[t];
+            for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+            l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+            u = dm::nmax_(u, dm::max0_(y - c.y_ub));
         }
         cs[r] = warp_nmax(m); lbv[r] = warp_nmax(l); ubv[r] = warp_nmax(u); beta[r] = a.beta[(size_t)g * nr + r];
     }

@@ -208,13 +208,11 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
         for (int r = 0; r < nr; r++) {
             float m = 0.0f, l = 0.0f, u = 0.0f;
-            for (int i = lane; i < c.O * np; i += 32) {
-                const int o = i / np, t = i % np;
-                m = dm::nmax_(m, fbar(c, xr[r * np + t], yr[r * np + t], xo[o * T_ + t], yo[o * T_ + t]));
-            }
-            for (int t = lane; t < np; t += 32) {
-                l = dm::nmax_(l, dm::max0_(-yr[r * np + t] + c.y_lb));
-                u = dm::nmax_(u, dm::max0_(yr[r * np + t] - c.y_ub));
+            for (int t = lane; t < np; t += 32) {          // lane owns timesteps; the maxima are order independent (NaN propagates either way)
+                const float x = xr[r * np + t], y = yr[r * np + t];
+                for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+                l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+                u = dm::nmax_(u, dm::max0_(y - c.y_ub));
             }
             m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
             if (lane == 0) { cst[r] = m; lb[r] = l; ub[r] = u; }

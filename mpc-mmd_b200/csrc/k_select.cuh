@@ -25,6 +25,7 @@ struct SelArgs {
 };
 
 #define SEL_THREADS 128
+#define SEL_THREADS_BIG 1024
 #define SEL_RANK_MAX 1024   // up to this batch size the 64-bit keys are staged in shared memory and ranked by counting
 
 // (risk, res_norm, index) lexicographic "j before i", NaN last in each key
@@ -45,11 +46,11 @@ __device__ __forceinline__ uint32_t sel_key32(float x) {
     return k;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
+__global__ void __launch_bounds__(1024) k_select(DCfg c, SelArgs a) {      // SEL_THREADS threads, SEL_THREADS_BIG for batches above SEL_RANK_MAX
     extern __shared__ __align__(16) float sm[];    // 64-bit composite keys [B]
     const int e = blockIdx.x;
     if (e >= a.n_ep) return;
-    const int B = a.B, tid = threadIdx.x, n20 = c.n_el_cost, n5 = c.n_el;
+    const int B = a.B, tid = threadIdx.x, nthr = blockDim.x, n20 = c.n_el_cost, n5 = c.n_el;
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);
     __shared__ int top[32], el[8];
     __shared__ float cost20[32], th[8][NPAR], L[NPAR * NPAR], mean_new[NPAR], wts[8], s_sumw;
@@ -57,9 +58,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
     const float* risk = a.risk + (size_t)e * B; const float* res = a.res_norm + (size_t)e * B;
     // position of sample i after the two stable argsorts = rank of (risk, res_norm, index): one 64-bit compare per pair
     if (B <= SEL_RANK_MAX) {
-        for (int i = tid; i < B; i += SEL_THREADS) skey[i] = ((unsigned long long)sel_key32(risk[i]) << 32) | (unsigned long long)sel_key32(res[i]);
+        for (int i = tid; i < B; i += nthr) skey[i] = ((unsigned long long)sel_key32(risk[i]) << 32) | (unsigned long long)sel_key32(res[i]);
         __syncthreads();
-        for (int i = tid; i < B; i += SEL_THREADS) {
+        for (int i = tid; i < B; i += nthr) {
             const unsigned long long ki = skey[i];
             int rank = 0;
 #pragma unroll 4
@@ -70,15 +71,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
         // large batches (scaled configurations): only the first n_el_cost positions are needed, so take them by n_el_cost rounds of
         // "smallest (key, index) above the previous winner" -- O(n_el_cost * B) instead of the O(B^2) rank count; keys are recomputed
         // from global memory (L2-resident) instead of being staged in shared memory
-        __shared__ unsigned long long wk[SEL_THREADS / 32];
-        __shared__ int wi[SEL_THREADS / 32];
+        __shared__ unsigned long long wk[32];
+        __shared__ int wi[32];
         __shared__ unsigned long long last_k; __shared__ int last_i;
         if (tid == 0) { last_k = 0ull; last_i = -1; }
         __syncthreads();
         for (int r = 0; r < n20; r++) {
             const unsigned long long lk = last_k; const int li = last_i;
             unsigned long long bk = ~0ull; int bi = 0x7fffffff;
-            for (int j = tid; j < B; j += SEL_THREADS) {
+            for (int j = tid; j < B; j += nthr) {
                 const unsigned long long kj = ((unsigned long long)sel_key32(risk[j]) << 32) | (unsigned long long)sel_key32(res[j]);
                 const bool above = (r == 0) || kj > lk || (kj == lk && j > li);
                 if (above && (kj < bk || (kj == bk && j < bi))) { bk = kj; bi = j; }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(DCfg c, SelArgs a) {
             if ((tid & 31) == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
             __syncthreads();
             if (tid == 0) {
-                for (int w2 = 1; w2 < SEL_THREADS / 32; w2++) if (wk[w2] < bk || (wk[w2] == bk && wi[w2] < bi)) { bk = wk[w2]; bi = wi[w2]; }
+                for (int w2 = 1; w2 < nthr / 32; w2++) if (wk[w2] < bk || (wk[w2] == bk && wi[w2] < bi)) { bk = wk[w2]; bi = wi[w2]; }
                 top[r] = bi; last_k = bk; last_i = bi;
             }
             __syncthreads();

@@ -330,8 +330,8 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
     int cnt = 0;
     auto mark = [&](int cls) { cnt++; if (marks) { LaunchMark m; cudaEventCreate(&m.ev); cudaEventRecord(m.ev, s); m.cls = cls; marks->push_back(m); } };
     k_boundary<<<(n_ep + 127) / 128, 128, 0, s>>>(w.init_state, h->beq_x, h->beq_y, h->state0, n_ep); mark(0);
-    k_noise<<<n_ep * d.iters, 128, 0, s>>>(d, w, n_ep, 0, d.iters); mark(0);
-    k_init<<<n_ep, 128, 0, s>>>(d, w, n_ep); mark(0);
+    k_noise<<<n_ep * d.iters, d.B <= SEL_RANK_MAX ? 128 : 1024, 0, s>>>(d, w, n_ep, 0, d.iters); mark(0);
+    k_init<<<n_ep, d.B <= SEL_RANK_MAX ? 128 : 1024, 0, s>>>(d, w, n_ep); mark(0);
     for (int it = 0; it < d.iters; it++) {
         ProjArgs p = proj_args(h, n_ep);
         launch_project(h, p, s); mark(1);
@@ -350,7 +350,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         a.zcem = w.zcem + it * ncem; a.z_stride = (size_t)d.iters * ncem; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma;
         a.res_beta = w.res_beta; a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta;
         a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta; a.o_sel = w.o_sel; a.sel_stride = d.iters;
-        k_select<<<n_ep, SEL_THREADS, sel_smem(d), s>>>(d, a); mark(3);
+        k_select<<<n_ep, d.B <= SEL_RANK_MAX ? SEL_THREADS : SEL_THREADS_BIG, sel_smem(d), s>>>(d, a); mark(3);
     }
     *launches = cnt;
     return 0;
@@ -521,7 +521,7 @@ extern "C" int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float* 
     a.zcem = z_cem; a.z_stride = 0; a.cx = w.cx; a.cy = w.cy; a.beta = w.beta; a.sigma = w.sigma; a.res_beta = w.res_beta;
     a.o_cx = w.o_cx; a.o_cy = w.o_cy; a.o_lane = w.o_lane; a.o_obs = w.o_obs; a.o_beta = w.o_beta; a.o_sigma = w.o_sigma; a.o_res_beta = w.o_res_beta;
     a.o_sel = sel; a.sel_stride = 1;
-    k_select<<<1, SEL_THREADS, sel_smem(d)>>>(d, a);
+    k_select<<<1, d.B <= SEL_RANK_MAX ? SEL_THREADS : SEL_THREADS_BIG, sel_smem(d)>>>(d, a);
     CK(cudaDeviceSynchronize());
     return 0;
 }
