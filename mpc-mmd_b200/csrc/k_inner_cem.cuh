@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(OPT_RISK_WARPS * 32) k_opt_risk(DCfg c, RollAr
         float m = 0.0f, l = 0.0f, u = 0.0f;
         for (int t = lane; t < np; t += 32) {
             const float x = xred[t], y = yred[t];
-            for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+            _Pragma("unroll 4") for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
             l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
             u = dm::nmax_(u, dm::max0_(y - c.y_ub));
         }

@@ -31,10 +31,11 @@ struct RiskArgs {
 __device__ __forceinline__ void rollout_one(const DCfg& c, const float* a, const float* s, const float* st0, float* xr, float* yr) {
     float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
     for (int t = 0; t < c.np; t++) {
+        const float at = a[t], st = s[t];       // read before the stores: xr / yr may alias a / s (num_reduced-rollout costs)
         xr[t] = x; yr[t] = y;
         float v = sqrtf(vx * vx + vy * vy);
-        v = v + a[t] * c.dt;
-        float psidot = (v * dm::tan_(s[t])) / c.wheel_base;
+        v = v + at * c.dt;
+        float psidot = (v * dm::tan_(st)) / c.wheel_base;
         psi = psi + psidot * c.dt;
         float sp, cp; dm::sincos_(psi, sp, cp);
         vx = v * cp; vy = v * sp;
@@ -125,7 +126,9 @@ struct RollArgs {
     float* bscratch;         // [n][S][nr + 1]  per-row beta vectors and packed reduced-set indices of k_inner_cem_fast's current iteration
 };
 __host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }       // per-rollout cost / lane-lb / lane-ub slots
-__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + 2 * R * np + 4 * roll_tail_floats(nr)); }
+// per sample: noisy controls (2 x nr x np), rollouts (2 x R x np), cost slots.  With R == nr (cvar / saa / mmd_random) rollout r reads only
+// control row r, so the rollouts overwrite the controls in place and the sample needs half the space (twice the resident CTAs).
+__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + (R == nr ? 0 : 2 * R * np) + 4 * roll_tail_floats(nr)); }
 
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
@@ -135,7 +138,9 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
     const int g0 = blockIdx.x * spb;
     const int ns = min(spb, a.n_samples - g0);                 // samples in this CTA
     if (ns <= 0) return;
-    const int tail = roll_tail_floats(nr), per = 2 * n + 2 * R * np + 4 * tail;
+    const bool opt = a.cost_kind == 0;
+    const int tail = roll_tail_floats(nr), xoff = opt ? 2 * n : 0, yoff = opt ? 2 * n + R * np : n, coff = opt ? 2 * n + 2 * R * np : 2 * n;
+    const int per = coff + 4 * tail;
     // ---- perturbed controls  [cem_helper.py:405-443 / 470-508]
 #pragma unroll 1
     for (int i = tid; i < ns * n; i += nt) {
@@ -167,11 +172,10 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
     }
     __syncthreads();
     // ---- rollouts: thread (sample, rollout); mmd_opt mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
-    const bool opt = a.cost_kind == 0;
 #pragma unroll 1
     for (int i = tid; i < ns * R; i += nt) {
         const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
-        float* an = sm + ls * per; float* sn = an + n; float* xr = sn + n; float* yr = xr + R * np;
+        float* an = sm + ls * per; float* sn = an + n; float* xr = an + xoff; float* yr = an + yoff;
         const int ia = opt ? m / nr : m, is = opt ? m % nr : m;
         rollout_one(c, an + ia * np, sn + is * np, a.state0 + e * 5, xr + m * np, yr + m * np);
     }
@@ -202,15 +206,15 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
     for (int ls = warp; ls < ns; ls += nt / 32) {
         const int g = g0 + ls, e = g / a.B;
-        const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
-        float* cst = sm + ls * per + 2 * n + 2 * R * np; float* lb = cst + tail; float* ub = lb + tail; float* bet = ub + tail;
+        const float* xr = sm + ls * per + xoff; const float* yr = sm + ls * per + yoff;
+        float* cst = sm + ls * per + coff; float* lb = cst + tail; float* ub = lb + tail; float* bet = ub + tail;
         const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
 #pragma unroll 1
         for (int r = 0; r < nr; r++) {
             float m = 0.0f, l = 0.0f, u = 0.0f;
             for (int t = lane; t < np; t += 32) {          // lane owns timesteps; the maxima are order independent (NaN propagates either way)
                 const float x = xr[r * np + t], y = yr[r * np + t];
-                for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+                _Pragma("unroll 4") for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
                 l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
                 u = dm::nmax_(u, dm::max0_(y - c.y_ub));
             }
