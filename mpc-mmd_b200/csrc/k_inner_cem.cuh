@@ -605,33 +605,31 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
     if (tid == 0) a.sigma[g] = small[48];
 }
 
-// risk of the reduced set k_inner_cem_fast chose (its rollouts come back from global memory): one warp per sample  [costs.py:173-186, 121-135]
-#define OPT_RISK_WARPS 4
-__global__ void __launch_bounds__(OPT_RISK_WARPS * 32) k_opt_risk(DCfg c, RollArgs ra) {
+// risk of the reduced set k_inner_cem_fast chose  [costs.py:173-186, 121-135]: thread (sample, r) re-rolls reduced rollout r from the
+// sample's noisy controls (same arithmetic as the mother rollout => same bits) with the obstacle / lane maxima folded in, then one thread per
+// sample evaluates the three MMD values.  The mother rollouts themselves are never stored.
+#define OPT_RISK_THREADS 128
+__global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs ra) {
+    __shared__ float vals[3 * OPT_RISK_THREADS];
     const RiskArgs& a = ra.r;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * OPT_RISK_WARPS + warp;
-    if (g >= a.n_samples) return;
-    const int e = g / a.B, np = c.np, nr = c.nr, nm = c.nm;
-    const int* ridx = ra.ridx + (size_t)g * nr;
-    const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
-    const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    float cs[MPCMMD_MAX_NR], lbv[MPCMMD_MAX_NR], ubv[MPCMMD_MAX_NR], beta[MPCMMD_MAX_NR];
-#pragma unroll 1
-    for (int r = 0; r < nr; r++) {
-        const float* xred = xg + ridx[r] * np; const float* yred = yg + ridx[r] * np;
-        float m = 0.0f, l = 0.0f, u = 0.0f;
-        for (int t = lane; t < np; t += 32) {
-            const float x = xred[t], y = yred[t];
-            _Pragma("unroll 4") for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
-            l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
-            u = dm::nmax_(u, dm::max0_(y - c.y_ub));
-        }
-        cs[r] = warp_nmax(m); lbv[r] = warp_nmax(l); ubv[r] = warp_nmax(u); beta[r] = a.beta[(size_t)g * nr + r];
+    const int nr = c.nr, np = c.np, n = nr * np, tid = threadIdx.x;
+    const int spb = OPT_RISK_THREADS / nr;
+    const int ls = tid / nr, r = tid % nr, g = blockIdx.x * spb + ls;
+    const bool live = ls < spb && g < a.n_samples;
+    if (live) {
+        const int e = g / a.B, mi = ra.ridx[(size_t)g * nr + r];
+        const float* ct = ra.ctrl + (size_t)g * 2 * n;
+        float m, l, u;
+        rollout_risk<false>(c, a, g, e, 0, ct + (mi / nr) * np, ct + n + (mi % nr) * np, a.state0 + e * 5,
+                            a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
+        vals[tid] = m; vals[OPT_RISK_THREADS + tid] = l; vals[2 * OPT_RISK_THREADS + tid] = u;
     }
-    if (lane == 0) {
+    __syncthreads();
+    if (live && r == 0) {
+        float beta[MPCMMD_MAX_NR];
+        for (int i = 0; i < nr; i++) beta[i] = a.beta[(size_t)g * nr + i];
         const float sigma = a.sigma[g];
-        a.risk[g] = mmd_cost(c, beta, cs, sigma);
-        a.lane[g] = mmd_cost(c, beta, lbv, sigma) + mmd_cost(c, beta, ubv, sigma);
+        a.risk[g] = mmd_cost(c, beta, vals + tid, sigma);
+        a.lane[g] = mmd_cost(c, beta, vals + OPT_RISK_THREADS + tid, sigma) + mmd_cost(c, beta, vals + 2 * OPT_RISK_THREADS + tid, sigma);
     }
 }

@@ -27,26 +27,42 @@ struct RiskArgs {
     float *beta, *sigma, *res_beta;  // [n][nr], [n], [n][iters_in]
 };
 
-// Euler bicycle rollout, records the state BEFORE each step  [cem_helper.py:380-400, 451-458]
-__device__ __forceinline__ void rollout_one(const DCfg& c, const float* a, const float* s, const float* st0, float* xr, float* yr) {
-    float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
-    for (int t = 0; t < c.np; t++) {
-        const float at = a[t], st = s[t];       // read before the stores: xr / yr may alias a / s (num_reduced-rollout costs)
-        xr[t] = x; yr[t] = y;
-        float v = sqrtf(vx * vx + vy * vy);
-        v = v + at * c.dt;
-        float psidot = (v * dm::tan_(st)) / c.wheel_base;
-        psi = psi + psidot * c.dt;
-        float sp, cp; dm::sincos_(psi, sp, cp);
-        vx = v * cp; vy = v * sp;
-        x = x + vx * c.dt; y = y + vy * c.dt;
-    }
-}
 // obstacle indicator at one (rollout point, obstacle point)  [costs.py:50-60]
 __device__ __forceinline__ float fbar(const DCfg& c, float x, float y, float xo, float yo) {
     float wc = x - xo, ws = y - yo;
     float cost = (-(wc * wc) / c.a2_obs - (ws * ws) / c.b2_obs) + 1.0f;
     return dm::max0_(cost);
+}
+// one step of the Euler bicycle model  [cem_helper.py:380-400]
+__device__ __forceinline__ void bicycle_step(const DCfg& c, float a, float s, float& x, float& y, float& vx, float& vy, float& psi) {
+    float v = sqrtf(vx * vx + vy * vy);
+    v = v + a * c.dt;
+    float psidot = (v * dm::tan_(s)) / c.wheel_base;
+    psi = psi + psidot * c.dt;
+    float sp, cp; dm::sincos_(psi, sp, cp);
+    vx = v * cp; vy = v * sp;
+    x = x + vx * c.dt; y = y + vy * c.dt;
+}
+// rollout of a mother sample of mmd_opt: the 22 ridge-fit features (cem_helper.py:553-564, folded: feature_k = sum_t Wfit[k][t] * x[t],
+// ascending t -- the contract's order) are accumulated while the state advances; the 22 independent fma chains fill the issue slots the
+// serial sqrt -> tan -> sincos chain leaves empty.  Positions are written only for the kernels that still read them back (WRITE).
+template <bool WRITE>
+__device__ __forceinline__ void rollout_fit(const DCfg& c, const float* a, const float* s, const float* st0, const float* __restrict__ W /* (11,np) */,
+                                            float* __restrict__ xg, float* __restrict__ yg, float* __restrict__ feat) {
+    float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
+    float fx[NV], fy[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) { fx[k] = 0.0f; fy[k] = 0.0f; }
+    const int np = c.np;
+#pragma unroll 1
+    for (int t = 0; t < np; t++) {          // the state BEFORE step t is the recorded point  [cem_helper.py:451-458]
+        if (WRITE) { xg[t] = x; yg[t] = y; }
+#pragma unroll
+        for (int k = 0; k < NV; k++) { const float w = W[k * np + t]; fx[k] = fmaf(w, x, fx[k]); fy[k] = fmaf(w, y, fy[k]); }
+        bicycle_step(c, a[t], s[t], x, y, vx, vy, psi);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) { feat[k] = fx[k]; feat[NV + k] = fy[k]; }
 }
 // Laplace-kernel MMD of nr scalar costs against the zero cost  [kernel_computation.py:67-87]
 __device__ __noinline__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, float sigma) {
@@ -119,17 +135,73 @@ struct RollArgs {
     RiskArgs r;
     int spb;                 // samples per CTA
     int R;                   // rollouts per sample (nr or nr*nr)
-    float *xroll, *yroll;    // [n][R][np]   (mmd_opt only)
+    int stage_ctrl;          // cvar / saa / mmd_random: draw the noisy controls into shared memory with the whole CTA first (latency regime: few samples)
+    int write_rolls;         // mmd_opt: also write the mother rollouts (only the generic / warp-per-chain inner kernels read them back)
+    float *xroll, *yroll;    // [n][R][np]   (mmd_opt, write_rolls only)
     float* feat;             // [n][nm][22]  (mmd_opt only)
+    float* ctrl;             // [n][2][nr*np]  noisy controls of the sample (mmd_opt): k_opt_risk re-rolls the chosen reduced set from them
     float* stash;            // [persistent CTAs][S][32]  row stash of k_inner_cem_warp
     int* ridx;               // [n][nr]  reduced set chosen by k_inner_cem_fast, read by k_opt_risk
     float* bscratch;         // [n][S][nr + 1]  per-row beta vectors and packed reduced-set indices of k_inner_cem_fast's current iteration
 };
-__host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }       // per-rollout cost / lane-lb / lane-ub slots
-// per sample: noisy controls (2 x nr x np), rollouts (2 x R x np), cost slots.  With R == nr (cvar / saa / mmd_random) rollout r reads only
-// control row r, so the rollouts overwrite the controls in place and the sample needs half the space (twice the resident CTAs).
-__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R) { return spb * (2 * nr * np + (R == nr ? 0 : 2 * R * np) + 4 * roll_tail_floats(nr)); }
+// mmd_opt: noisy controls of the CTA's samples (2 x nr x np each) + the ridge-fit matrix; the other costs: 4 slots of per-rollout values
+__host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }
+__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R, int stage_ctrl = 0) {
+    return R == nr ? spb * (4 * roll_tail_floats(nr) + (stage_ctrl ? 2 * nr * np : 0)) : spb * 2 * nr * np + ((NV * np + 3) & ~3);
+}
 
+// noisy control pair of element el = row * np + t of sample g  [cem_helper.py:405-443 / 470-508]
+__device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, int g, int e, int el, int t, int n, float& an, float& sn) {
+    const float av = a.acc[(size_t)g * T_ + t], sv = a.steer[(size_t)g * T_ + t];
+    const float* z3 = a.z3 + e * a.z_stride;
+    float pa, ps;
+    if (c.noise_kind == 0) {
+        pa = (c.sigma_acc * fabsf(av)) * (a.z1 + e * a.z_stride)[el];
+        ps = (c.sigma_steer * fabsf(sv)) * (a.z2 + e * a.z_stride)[el];
+    } else {
+        const uint32_t* keys = a.keys + e * a.key_stride;
+        dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
+        float b1, b2;
+        if (a.btab) {
+            const float* bt = a.btab + e * a.btab_stride;
+            b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+            b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+        } else {
+            b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+            b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+        }
+        pa = c.sigma_acc * (2.0f * b1 - 1.0f);
+        ps = c.ksig_steer * (2.0f * b2 - 1.0f);
+    }
+    an = (av + pa) + c.acc_const * z3[el];
+    sn = (sv + ps) + c.steer_const * z3[el];
+}
+
+// one rollout with its obstacle / lane indicators folded in: m = max over (obstacle, t) of f_bar, l / u = max over t of the lane violations,
+// each evaluated on the state BEFORE step t (the recorded point).  The maxima are order independent (NaN propagates either way), so this equals
+// the reference's "roll out, then reduce" [costs.py:50-71].  FLY: the controls of row `row` are drawn inside the loop (costs with one control row
+// per rollout); otherwise they are read from a / s.
+template <bool FLY>
+__device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, int g, int e, int row, const float* a, const float* s,
+                                             const float* st0, const float* __restrict__ xo, const float* __restrict__ yo, float& m, float& l, float& u) {
+    float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
+    const int np = c.np, n = c.nr * np;
+    m = 0.0f; l = 0.0f; u = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < np; t++) {
+        float at, st;
+        if (FLY) noisy_control(c, A, g, e, row * np + t, t, n, at, st); else { at = a[t]; st = s[t]; }
+#pragma unroll 4
+        for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+        l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+        u = dm::nmax_(u, dm::max0_(y - c.y_ub));
+        bicycle_step(c, at, st, x, y, vx, vy, psi);
+    }
+}
+
+// MODE 0: mmd_opt; 1: num_reduced-rollout costs, throughput regime; 2: the same, latency regime.  Three instantiations keep each launch's code small.
+enum { ROLL_OPT = 0, ROLL_FLY = 1, ROLL_STAGED = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
     const RiskArgs& a = ra.r;
@@ -138,90 +210,93 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
     const int g0 = blockIdx.x * spb;
     const int ns = min(spb, a.n_samples - g0);                 // samples in this CTA
     if (ns <= 0) return;
-    const bool opt = a.cost_kind == 0;
-    const int tail = roll_tail_floats(nr), xoff = opt ? 2 * n : 0, yoff = opt ? 2 * n + R * np : n, coff = opt ? 2 * n + 2 * R * np : 2 * n;
-    const int per = coff + 4 * tail;
-    // ---- perturbed controls  [cem_helper.py:405-443 / 470-508]
+    if constexpr (MODE == ROLL_OPT) {
+        // ================= mmd_opt: noisy controls -> num_reduced^2 mother rollouts -> ridge-fit features =================
+        float* sW = sm + spb * 2 * n;
 #pragma unroll 1
-    for (int i = tid; i < ns * n; i += nt) {
-        const int ls = i / n, el = i % n, t = el % np, g = g0 + ls, e = g / a.B;
-        float* an = sm + ls * per; float* sn = an + n;
-        const float av = a.acc[(size_t)g * T_ + t], sv = a.steer[(size_t)g * T_ + t];
-        const float* z3 = a.z3 + e * a.z_stride;
-        float pa, ps;
-        if (c.noise_kind == 0) {
-            pa = (c.sigma_acc * fabsf(av)) * (a.z1 + e * a.z_stride)[el];
-            ps = (c.sigma_steer * fabsf(sv)) * (a.z2 + e * a.z_stride)[el];
-        } else {
-            const uint32_t* keys = a.keys + e * a.key_stride;
-            dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
-            float b1, b2;
-            if (a.btab) {
-                const float* bt = a.btab + e * a.btab_stride;
-                b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
-                b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
-            } else {
-                b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
-                b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+        for (int i = tid; i < NV * np; i += nt) sW[i] = c.Wfit[i];
+#pragma unroll 1
+        for (int i = tid; i < ns * n; i += nt) {
+            const int ls = i / n, el = i % n, g = g0 + ls;
+            float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
+            sm[ls * 2 * n + el] = an; sm[ls * 2 * n + n + el] = sn;
+            ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = sn;
+        }
+        __syncthreads();
+        // mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
+#pragma unroll 1
+        for (int i = tid; i < ns * R; i += nt) {
+            const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
+            const float* an = sm + ls * 2 * n + (m / nr) * np; const float* sn = sm + ls * 2 * n + n + (m % nr) * np;
+            float* ft = ra.feat + ((size_t)g * R + m) * 2 * NV;
+            if (ra.write_rolls) rollout_fit<true>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
+            else rollout_fit<false>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft);
+        }
+    } else {
+    // ================= cvar / saa / mmd_random: one thread per (sample, rollout), controls drawn inside the rollout =================
+    // Throughput regime: every thread draws its rollout's controls inside the loop (no staging, 25 samples per CTA).  Latency regime (a launch
+    // too small to fill the GPU): the 2 x nr x np draws of a sample are spread over the whole CTA first, then nr threads roll out.
+    const int tail = roll_tail_floats(nr), per = 4 * tail + (MODE == ROLL_STAGED ? 2 * n : 0);
+    if constexpr (MODE == ROLL_STAGED) {
+#pragma unroll 1
+        for (int i = tid; i < ns * n; i += nt) {
+            const int ls = i / n, el = i % n, g = g0 + ls;
+            float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
+            sm[ls * per + 4 * tail + el] = an; sm[ls * per + 4 * tail + n + el] = sn;
+        }
+        __syncthreads();
+    }
+    if constexpr (MODE == ROLL_STAGED) {
+        // rollouts overwrite their own control rows in place (rollout r reads only row r), then one warp per sample reduces the obstacle / lane
+        // indicators with a lane per timestep: the serial part of the CTA is just the np bicycle steps
+#pragma unroll 1
+        for (int i = tid; i < ns * R; i += nt) {
+            const int ls = i / R, r = i % R, e = (g0 + ls) / a.B;
+            float* an = sm + ls * per + 4 * tail + r * np; float* sn = an + n;
+            float x = a.state0[e * 5], y = a.state0[e * 5 + 1], vx = a.state0[e * 5 + 2], vy = a.state0[e * 5 + 3], psi = a.state0[e * 5 + 4];
+            for (int t = 0; t < np; t++) {
+                const float at = an[t], st = sn[t];
+                an[t] = x; sn[t] = y;
+                bicycle_step(c, at, st, x, y, vx, vy, psi);
             }
-            pa = c.sigma_acc * (2.0f * b1 - 1.0f);
-            ps = c.ksig_steer * (2.0f * b2 - 1.0f);
         }
-        an[el] = (av + pa) + c.acc_const * z3[el];
-        sn[el] = (sv + ps) + c.steer_const * z3[el];
+        __syncthreads();
+#pragma unroll 1
+        for (int ls = warp; ls < ns; ls += nt / 32) {
+            const int e = (g0 + ls) / a.B;
+            const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
+            float* cst = sm + ls * per;
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                const float* xr = sm + ls * per + 4 * tail + r * np; const float* yr = xr + n;
+                float m = 0.0f, l = 0.0f, u = 0.0f;
+                for (int t = lane; t < np; t += 32) {
+                    const float x = xr[t], y = yr[t];
+#pragma unroll 4
+                    for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+                    l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+                    u = dm::nmax_(u, dm::max0_(y - c.y_ub));
+                }
+                m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
+                if (lane == 0) { cst[r] = m; cst[tail + r] = l; cst[2 * tail + r] = u; }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = tid; i < ns * R; i += nt) {
+            const int ls = i / R, r = i % R, g = g0 + ls, e = g / a.B;
+            float m, l, u;
+            rollout_risk<true>(c, a, g, e, r, nullptr, nullptr, a.state0 + e * 5, a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
+            float* cst = sm + ls * per;
+            cst[r] = m; cst[tail + r] = l; cst[2 * tail + r] = u;
+        }
     }
     __syncthreads();
-    // ---- rollouts: thread (sample, rollout); mmd_opt mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
-#pragma unroll 1
-    for (int i = tid; i < ns * R; i += nt) {
-        const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
-        float* an = sm + ls * per; float* sn = an + n; float* xr = an + xoff; float* yr = an + yoff;
-        const int ia = opt ? m / nr : m, is = opt ? m % nr : m;
-        rollout_one(c, an + ia * np, sn + is * np, a.state0 + e * 5, xr + m * np, yr + m * np);
-    }
-    __syncthreads();
-    if (opt) {
-        // ---- mother rollouts + ridge-fit features to global  [cem_helper.py:553-564, folded]
-        const int nm = R;
-#pragma unroll 1
-        for (int i = tid; i < ns * nm * np; i += nt) {
-            const int ls = i / (nm * np), rem = i % (nm * np);
-            const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
-            ra.xroll[(size_t)(g0 + ls) * nm * np + rem] = xr[rem];
-            ra.yroll[(size_t)(g0 + ls) * nm * np + rem] = yr[rem];
-        }
-#pragma unroll 1
-        for (int i = tid; i < ns * nm * 2 * NV; i += nt) {
-            const int ls = i / (nm * 2 * NV), rem = i % (nm * 2 * NV), m = rem / (2 * NV), k = rem % (2 * NV);
-            const float* xr = sm + ls * per + 2 * n; const float* yr = xr + R * np;
-            const float* src = (k < NV) ? xr + m * np : yr + m * np;
-            const float* W = c.Wfit + (k < NV ? k : k - NV) * np;
-            float acc = 0.0f;
-            for (int t = 0; t < np; t++) acc = fmaf(__ldg(W + t), src[t], acc);
-            ra.feat[(size_t)(g0 + ls) * nm * 2 * NV + rem] = acc;
-        }
-        return;
-    }
-    // ---- risk of the nr rollouts (one warp per sample at a time)  [costs.py:50-71, 137-234; cem.py:355-356]
+    // ---- risk functional of the nr per-rollout values (one warp per sample at a time)  [costs.py:137-234; cem.py:355-356]
 #pragma unroll 1
     for (int ls = warp; ls < ns; ls += nt / 32) {
-        const int g = g0 + ls, e = g / a.B;
-        const float* xr = sm + ls * per + xoff; const float* yr = sm + ls * per + yoff;
-        float* cst = sm + ls * per + coff; float* lb = cst + tail; float* ub = lb + tail; float* bet = ub + tail;
-        const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-#pragma unroll 1
-        for (int r = 0; r < nr; r++) {
-            float m = 0.0f, l = 0.0f, u = 0.0f;
-            for (int t = lane; t < np; t += 32) {          // lane owns timesteps; the maxima are order independent (NaN propagates either way)
-                const float x = xr[r * np + t], y = yr[r * np + t];
-                _Pragma("unroll 4") for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
-                l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
-                u = dm::nmax_(u, dm::max0_(y - c.y_ub));
-            }
-            m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
-            if (lane == 0) { cst[r] = m; lb[r] = l; ub[r] = u; }
-        }
-        __syncwarp();
+        const int g = g0 + ls;
+        float* cst = sm + ls * per; float* lb = cst + tail; float* ub = lb + tail; float* bet = ub + tail;
         if (a.cost_kind == 1) {                           // mmd_random: beta = 1/nr, sigma = 0.01, lane = 0  [cem.py:355-356, 404-424]
             for (int i = lane; i < nr; i += 32) { bet[i] = c.beta_del; a.beta[(size_t)g * nr + i] = c.beta_del; }
             __syncwarp();
@@ -240,6 +315,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             }
             a.risk[g] = risk; a.lane[g] = lanec;
         }
+    }
     }
 }
 

@@ -30,8 +30,10 @@ struct mpcmmd_handle_s {
     DWork w;
     float *beq_x = nullptr, *beq_y = nullptr, *state0 = nullptr;   // [E][3], [E][4], [E][5]
     float *xroll = nullptr, *yroll = nullptr, *feat = nullptr;     // mmd_opt scratch (ensure_opt_scratch)
+    float *rolls_x = nullptr, *rolls_y = nullptr;                  // [E*B][nm][np] mother rollouts (generic / warp-per-chain inner kernels only)
     int* ridx = nullptr;       // [E*B][nr] reduced sets (k_inner_cem_fast -> k_opt_risk)
     float* bscratch = nullptr; // [E*B][S][nr+1] row records of k_inner_cem_fast
+    float* ctrl = nullptr;     // [E*B][2][nr*np] noisy controls (k_rollouts -> k_opt_risk)
     float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
     int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
     int sm_count = 148;
@@ -80,19 +82,30 @@ static bool inner_cem_is_fast(const DCfg& d) {
 }
 // samples per CTA of k_rollouts: as many as keep one thread per rollout busy (bounded by shared memory), but never so
 // many that a small batch leaves SMs idle (latency at batch = 1 episode)
+// latency regime of the num_reduced-rollout costs: with one thread per rollout the launch cannot fill the GPU, so the controls are drawn by
+// whole CTAs first (RollArgs::stage_ctrl)
+static int roll_stage_ctrl(const DCfg& d, int kind, int n_samples) {
+    return kind != MPCMMD_COST_MMD_OPT && (long long)n_samples * d.nr < 2LL * 148 * ROLL_THREADS;
+}
 static int roll_spb(const DCfg& d, int kind, int n_samples) {
     const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
-    int spb = ROLL_THREADS / R; if (spb < 1) spb = 1; if (spb > 8) spb = 8;
-    while (spb > 1 && (size_t)roll_smem_floats(spb, d.nr, d.np, R) * sizeof(float) > 96 * 1024) spb--;
+    const int stage = roll_stage_ctrl(d, kind, n_samples);
+    int spb = ROLL_THREADS / R; if (spb < 1) spb = 1; if ((kind == MPCMMD_COST_MMD_OPT || stage) && spb > 8) spb = 8;
+    while (spb > 1 && (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage) * sizeof(float) > 96 * 1024) spb--;
     while (spb > 1 && (n_samples + spb - 1) / spb < 4 * 148) spb--;
     return spb;
 }
-static size_t roll_smem_for(const DCfg& d, int kind, int spb) {
+static size_t roll_smem_for(const DCfg& d, int kind, int spb, int stage) {
     const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
-    return (size_t)roll_smem_floats(spb, d.nr, d.np, R) * sizeof(float);
+    return (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage) * sizeof(float);
 }
-static size_t roll_smem(const DCfg& d, int kind) { return roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30)); }
-
+// largest dynamic shared memory any launch of this handle can ask for (opt-in at create)
+static size_t roll_smem(const DCfg& d, int kind) {
+    const size_t a = roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30), 0), b = roll_smem_for(d, kind, roll_spb(d, kind, 1), roll_stage_ctrl(d, kind, 1));
+    size_t c = 0;
+    for (int spb = 1; spb <= 8; spb++) { const size_t v = roll_smem_for(d, kind, spb, kind != MPCMMD_COST_MMD_OPT); if (v <= 96 * 1024 && v > c) c = v; }
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
 enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4 };
 static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
@@ -218,7 +231,9 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     {
         size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(d, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
-        if (rs > 48 * 1024 && cudaFuncSetAttribute(k_rollouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
+        if (rs > 48 * 1024 && (cudaFuncSetAttribute(k_rollouts<ROLL_OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess ||
+                               cudaFuncSetAttribute(k_rollouts<ROLL_FLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess ||
+                               cudaFuncSetAttribute(k_rollouts<ROLL_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess)) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
     }
     {
         const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
@@ -279,7 +294,12 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (h->xroll) return 0;
     if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10 (larger reduced sets: cvar / saa / mmd_random only)");
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
-    if (dalloc(h, &h->xroll, EB * d.nm * d.np) || dalloc(h, &h->yroll, EB * d.nm * d.np) || dalloc(h, &h->feat, EB * d.nm * 2 * NV)) return -1;
+    if (dalloc(h, &h->feat, EB * d.nm * 2 * NV) || dalloc(h, &h->ctrl, EB * 2 * d.nr * d.np)) return -1;
+    // the mother rollouts are stored only for the kernels that read them back (generic / warp-per-chain); allocated on first such launch
+    h->xroll = h->feat;     // non-null marker: scratch is ready
+    if (!inner_cem_is_fast(d) || h->inner_mode == INNER_WARP || h->inner_mode == INNER_GENERIC) {
+        if (dalloc(h, &h->rolls_x, EB * d.nm * d.np) || dalloc(h, &h->rolls_y, EB * d.nm * d.np)) return -1;
+    }
     if (dalloc(h, &h->ridx, EB * d.nr)) return -1;
     if (inner_cem_is_fast(d) && dalloc(h, &h->bscratch, EB * d.S_in * (d.nr + 1))) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
@@ -291,7 +311,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch;
+    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch; ra.ctrl = h->ctrl; ra.write_rolls = 0; ra.stage_ctrl = roll_stage_ctrl(d, r.cost_kind, r.n_samples);
     inner_cem_fn f = nullptr;
     int kind = INNER_GENERIC;
     if (opt) {
@@ -305,8 +325,17 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
+        if (kind != INNER_CTA && kind != INNER_CTA_LAT) {          // these kernels evaluate the risk themselves from the stored mother rollouts
+            if (!h->rolls_x) return fail("internal: mother-rollout scratch not allocated");
+            ra.write_rolls = 1; ra.xroll = h->rolls_x; ra.yroll = h->rolls_y;
+        }
     }
-    k_rollouts<<<(r.n_samples + ra.spb - 1) / ra.spb, ROLL_THREADS, roll_smem_for(d, r.cost_kind, ra.spb), s>>>(d, ra);
+    {
+        const int grid = (r.n_samples + ra.spb - 1) / ra.spb; const size_t rsm = roll_smem_for(d, r.cost_kind, ra.spb, ra.stage_ctrl);
+        if (opt) k_rollouts<ROLL_OPT><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
+        else if (ra.stage_ctrl) k_rollouts<ROLL_STAGED><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
+        else k_rollouts<ROLL_FLY><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
+    }
     if (n_launch) *n_launch = 1;
     if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
@@ -314,7 +343,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : RISKO_THREADS, sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
         if (kind == INNER_CTA || kind == INNER_CTA_LAT) {
-            k_opt_risk<<<(r.n_samples + OPT_RISK_WARPS - 1) / OPT_RISK_WARPS, OPT_RISK_WARPS * 32, 0, s>>>(d, ra);
+            { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
             if (n_launch) *n_launch = 3;
         }
     }
