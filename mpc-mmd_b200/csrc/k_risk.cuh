@@ -325,6 +325,8 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 // row => same arithmetic => same bits), so 96 threads are ~93 % busy in the sample stage and in the row-per-thread
 // resampling stage.
 #define RISKO_THREADS 96
+#define RISKO_THREADS_BIG 256     // num_reduced^2 + 1 > 32: one CTA per SM (100+ KB of shared memory), so the CTA itself has to fill the SM
+__host__ __device__ constexpr int risko_threads(int nr) { return nr * nr + 1 <= 32 ? RISKO_THREADS : RISKO_THREADS_BIG; }
 
 struct OptLayout {          // shared-memory carve-up (in floats); every offset is a multiple of 4 floats (16 B)
     int F, D, small, red, th, cost, betas, idxs, key64, perm, C, rd, mean, eth, xc, ecost, ebetas, eidxs;
@@ -337,7 +339,7 @@ __host__ __device__ inline OptLayout opt_layout(int nr, int np, int S, int ne) {
     L.ldc = al4(d);
     int q = 0;
     L.F = q; q += al4(nm * 2 * NV); L.D = q; q += al4(nm * nm); L.small = q; q += 64;
-    L.red = q; q += al4(3 * 16 * (RISKO_THREADS / 32));
+    L.red = q; q += al4(3 * 16 * (RISKO_THREADS_BIG / 32));
     L.th = q; q += al4(S * d); L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S * nr);
     L.key64 = q; q += al4(2 * S); L.perm = q; q += al4(S); L.C = q; q += al4(d * L.ldc); L.rd = q; q += al4(d); L.mean = q; q += al4(d);
     L.eth = q; q += al4(ne * d); L.xc = q; q += al4(ne * d); L.ecost = q; q += al4(ne); L.ebetas = q; q += al4(ne * nr); L.eidxs = q; q += al4(ne * nr);
@@ -448,14 +450,15 @@ __device__ __forceinline__ long long sort_key64(float x, int idx) {
 }
 
 template <int NR>
-__global__ void __launch_bounds__(RISKO_THREADS, (NR <= 5) ? 7 : 1) k_inner_cem(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_cem(DCfg c, RollArgs ra) {
     extern __shared__ __align__(16) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;
     constexpr int nm = NR * NR, d = nm + 1;
     constexpr bool SMALL = d <= 32;
-    const int tid = threadIdx.x, nt = RISKO_THREADS, warp = tid >> 5, lane = tid & 31;
+    constexpr int nt = risko_threads(NR);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int e = g / a.B, np = c.np, S = c.S_in, ne = c.n_el_in;
     const OptLayout L = opt_layout(NR, np, S, ne);
     const int ldc = L.ldc;
@@ -594,13 +597,48 @@ __global__ void __launch_bounds__(RISKO_THREADS, (NR <= 5) ? 7 : 1) k_inner_cem(
                 for (int r = j + 1 + tid; r < d; r += nt) C[r * ldc + j] = C[r * ldc + j] * rd[j];
                 __syncthreads();
             }
-            const float* z = c.zb_iter + (size_t)it * (S - ne) * d;
+            // -- L transposed into the (unused) upper triangle: C[k][q] = L[q][k] for q > k, so row k of C from column k on is column k of L
 #pragma unroll 1
-            for (int i = tid; i < (S - ne) * d; i += nt) {
-                const int r = i / d, q = i % d;
-                float v = mvn_elem(C, ldc, q, z + r * d, mean[q]);
-                if (q == nm) v = (v != v) ? v : (v > c.sigma_clip ? v : c.sigma_clip);
-                th[(ne + r) * d + q] = v;
+            for (int i = tid; i < d * d; i += nt) { const int q = i / d, k = i % d; if (k < q) C[k * ldc + q] = C[q * ldc + k]; }
+            __syncthreads();
+            // -- resample  [compute_beta.py:63-66]: task = (new row r, 8 consecutive columns q0..q0+7); acc_u = sum_{k <= q0+u} L[q0+u][k] z[r][k],
+            //    k ascending (the contract's chain), with the 8 columns of a step read as two float4 of row k.  Warps take consecutive r for one
+            //    column group: the L reads broadcast and the normals (a constant table, [iter][k][row]) are read coalesced from L1/L2.
+            const int nrow = S - ne;
+            const float* zT = c.zb_iterT + (size_t)it * d * nrow;
+            constexpr int NQ8 = (d + 7) / 8;
+#pragma unroll 1
+            for (int task = tid; task < NQ8 * nrow; task += nt) {
+                const int q0 = 8 * (task / nrow), r = task % nrow;
+                float acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = 0.0f;
+                const float* zp = zT + r;
+#pragma unroll 2
+                for (int k = 0; k <= q0; k++) {                 // every column of the group has q >= k
+                    const float z = __ldg(zp + (size_t)k * nrow);
+                    const float4 l0 = *reinterpret_cast<const float4*>(C + k * ldc + q0), l1 = *reinterpret_cast<const float4*>(C + k * ldc + q0 + 4);
+                    acc[0] = fmaf(l0.x, z, acc[0]); acc[1] = fmaf(l0.y, z, acc[1]); acc[2] = fmaf(l0.z, z, acc[2]); acc[3] = fmaf(l0.w, z, acc[3]);
+                    acc[4] = fmaf(l1.x, z, acc[4]); acc[5] = fmaf(l1.y, z, acc[5]); acc[6] = fmaf(l1.z, z, acc[6]); acc[7] = fmaf(l1.w, z, acc[7]);
+                }
+#pragma unroll
+                for (int kk = 1; kk < 8; kk++) {                // the triangle inside the group: column q0+u takes k = q0+kk only if u >= kk
+                    const int k = q0 + kk;
+                    if (k < d) {
+                        const float z = __ldg(zp + (size_t)k * nrow);
+#pragma unroll
+                        for (int u = kk; u < 8; u++) if (q0 + u < d) acc[u] = fmaf(C[k * ldc + q0 + u], z, acc[u]);
+                    }
+                }
+                float* dst = th + (ne + r) * d + q0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (q0 + u < d) {
+                        float v = mean[q0 + u] + acc[u];
+                        if (q0 + u == nm) v = (v != v) ? v : (v > c.sigma_clip ? v : c.sigma_clip);
+                        dst[u] = v;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -617,7 +655,7 @@ __global__ void __launch_bounds__(RISKO_THREADS, (NR <= 5) ? 7 : 1) k_inner_cem(
     const int* ridx = (const int*)small + 16;
     const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
     const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    constexpr int NW = RISKO_THREADS / 32;
+    constexpr int NW = nt / 32;
     float* red = sm + L.red;  // per-warp partial maxima, 3 * NR * NW floats
 #pragma unroll 1
     for (int r = 0; r < NR; r++) {

@@ -340,7 +340,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
         if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
-        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : RISKO_THREADS, sm, s>>>(d, ra);
+        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
         if (kind == INNER_CTA || kind == INNER_CTA_LAT) {
             { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }

@@ -136,7 +136,8 @@ def _controls(ora, rng, n):
 
 @pytest.mark.parametrize("cost,noise,nr,npr,nobs", [
     ("cvar", "gaussian", 5, 30, 2), ("cvar", "beta", 5, 50, 4), ("saa", "gaussian", 4, 20, 3), ("mmd_random", "gaussian", 5, 30, 2),
-    ("mmd_opt", "gaussian", 5, 30, 2), ("mmd_opt", "beta", 3, 20, 2), ("mmd_opt", "gaussian", 10, 40, 3), ("cvar", "gaussian", 10, 100, 6)])
+    ("mmd_opt", "gaussian", 5, 30, 2), ("mmd_opt", "beta", 3, 20, 2), ("mmd_opt", "gaussian", 10, 40, 3), ("cvar", "gaussian", 10, 100, 6),
+    ("mmd_opt", "beta", 6, 30, 2), ("mmd_opt", "gaussian", 8, 25, 3)])
 def test_stage_risk_bit_exact(mods, cost, noise, nr, npr, nobs):
     kw = dict(num_samples_cem=40, maxiter_beta_cem=4) if cost == "mmd_opt" else {}
     prob, ora = _pair(mods, (nr, nobs, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), **kw)
