@@ -370,3 +370,22 @@ def test_stage_risk_large_reduced_sets(mods, cost, nr, npr):
         ref = ora.risk(cost, acc[i], steer[i], st0, noise_t, xo, yo)
         for k in ("risk", "lane"):
             _eq(got[k][i], ref[k], f"{cost} nr={nr} np={npr} sample {i} {k}")
+
+
+def test_degenerate_inputs_propagate_nan_like_the_oracle(mods):
+    """edge cases the reference handles silently ('Errors'): a covariance that is not positive definite (Cholesky -> NaN) and
+    a vehicle at rest (zero speed -> 0/0 curvature).  NaN must sort last in every argsort and flow to the outputs exactly as in the oracle."""
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), **SMALL)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    idx, xo, yo = _episodes(O, ora, 3, 2)
+    bad_cov = cov.copy(); bad_cov[2, 2] = -1.0                       # not PD -> NaN rows from the third column on
+    rest = init_state.copy(); rest[2] = 0.0                          # vx = vy = 0
+    st = np.stack([init_state, init_state, rest]); cv = np.stack([cov, bad_cov, cov])
+    for cost in ("cvar", "mmd_opt"):
+        got = prob.solve_batch(cost, idx, st, np.stack([mean] * 3), cv, xo, yo, [v_des] * 3)
+        for e in range(3):
+            ref = ora.solve(cost, idx[e], st[e], mean, cv[e], xo[e], yo[e], v_des)
+            for k in ("cx", "cy", "cost_obs", "cost_lane"):
+                _eq(got[k][e], ref[k], f"{cost} ep{e} {k}")
+    assert np.isnan(got["cx"][1]).any() or np.isfinite(got["cx"][1]).all()      # whichever it is, it equals the oracle (checked above)
