@@ -389,3 +389,44 @@ def test_degenerate_inputs_propagate_nan_like_the_oracle(mods):
             for k in ("cx", "cy", "cost_obs", "cost_lane"):
                 _eq(got[k][e], ref[k], f"{cost} ep{e} {k}")
     assert np.isnan(got["cx"][1]).any() or np.isfinite(got["cx"][1]).all()      # whichever it is, it equals the oracle (checked above)
+
+
+@pytest.mark.parametrize("noise,level", [("gaussian", 0.1), ("beta", 0.3)])
+def test_solve_full_size_dynamic_mmd_opt_matches_oracle(mods, noise, level):
+    """BASELINE configs[2]: synthetic_dynamic_obs, mmd_opt, 6 obstacles, num_prime 60, full CEM sizes, episode 3 of the sweep (cut-in scene
+    from the dynamic generator); oracle ~10 s"""
+    cem_impl, O = mods
+    from mpcmmd_b200 import scenes
+    prob, ora = _pair(mods, (5, 6, level, 60, noise, 0.0, 0.0), variant="dynamic", max_episodes=1)
+    init_state, mean, cov, v_des = O.driver_inputs("dynamic")
+    _, idx, xt, yt = scenes.dynamic_scene(6, 3)
+    got = prob.compute_cem_mmd_opt(idx, init_state, mean, cov, xt, yt, v_des)
+    ref = ora.solve("mmd_opt", idx, init_state, mean, cov, xt, yt, v_des)
+    for g, k in zip(got, ("cx", "cy", "cost_lane", "cost_obs", "beta", "sigma", "res_beta")):
+        _eq(g, ref[k], f"{noise} {k}")
+
+
+def test_full_sweep_is_batch_invariant(mods):
+    """size-independent property at BASELINE configs[1] full size (200 episodes x 100 samples, both costs): an episode solved inside the
+    200-episode batch equals the same episode solved alone, bit for bit (episodes are independent), and the episode solved
+    alone equals the oracle (cvar)."""
+    cem_impl, O = mods
+    from mpcmmd_b200 import scenes
+    args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
+    big = cem_impl.CEM(*args, variant="static", max_episodes=200)
+    one = cem_impl.CEM(*args, variant="static", max_episodes=1)
+    batch = scenes.static_batch(big, list(range(200)))
+    pick = [0, 57, 131, 199]
+    for cost in ("cvar", "mmd_opt"):
+        out = big.solve_batch(cost, **batch)
+        assert out["cx"].shape == (200, 11) and np.isfinite(out["cx"]).all()
+        for k in pick:
+            solo = one.solve_batch(cost, **{n: v[k:k + 1] for n, v in batch.items()})
+            for f in ("cx", "cy", "cost_obs", "cost_lane") + (("beta", "sigma", "res_beta") if cost == "mmd_opt" else ()):
+                _eq(out[f][k], solo[f][0], f"{cost} episode {k} {f}: batch vs alone")
+    ora = O.OracleCEM(*args, variant="static")
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    out = big.solve_batch("cvar", **batch)
+    for k in pick:
+        ref = ora.solve("cvar", int(batch["idx_mpc"][k]), init_state, mean, cov, batch["x_obs_traj"][k], batch["y_obs_traj"][k], v_des)
+        _eq(out["cx"][k], ref["cx"], f"episode {k} cx vs oracle"); _eq(out["cost_obs"][k], ref["cost_obs"], f"episode {k} cost_obs vs oracle")
