@@ -21,6 +21,7 @@ struct DCfg {
     float lam_inv, one_m_alpha_mean, alpha_mean, one_m_alpha_cov, alpha_cov;
     float sigma_clip, inv_nm, m2_inv_nm, beta_del, sigma_random;
     const float *P, *Pd, *Pdd, *Gx, *Gy, *Kx, *Ky, *Wfit;   // device copies of the host constants
+    const float* proj_const;                                 // P | Pd | Pdd | Gx | Gy | Kx | Ky as ONE 16-byte-aligned block (bulk-copied into shared memory by k_project)
     const float *z_init, *theta0, *zb_iter;                  // constant normal tables (generated at create)
     const float *theta0T;                                    // theta0 transposed to [column][row]
     const float *zb_iterT;                                   // zb_iter transposed to [iter][column][row] for coalesced row-per-thread reads
@@ -51,6 +52,23 @@ struct DWork {
     float *o_cx, *o_cy, *o_lane, *o_obs, *o_beta, *o_sigma, *o_res_beta;
     int32_t *o_sel;                // [E][iters]
 };
+
+// ---- TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk, sm_90+): one elected thread issues the copy, every thread of
+// the CTA waits on the barrier's phase.  `bytes` must be a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // xor-butterfly sum over the 32 lanes (every lane ends with the same value; matches the oracle's
 // lane_sum_sq combine order 16,8,4,2,1)

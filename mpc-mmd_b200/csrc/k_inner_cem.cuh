@@ -462,7 +462,7 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
 
 template <int NR, bool LAT>
 __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, RollArgs ra) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;

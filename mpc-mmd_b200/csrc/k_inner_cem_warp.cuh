@@ -33,7 +33,7 @@ __host__ __device__ inline WarpLayout warp_layout(int nr, int S, int ne) {
 
 template <int NR>
 __global__ void __launch_bounds__(32, 20) k_inner_cem_warp(DCfg c, RollArgs ra) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     constexpr int nm = NR * NR, d = nm + 1, NG = (d + 3) / 4, NPAIR = (d + 1) / 2;
     static_assert(d <= ICW_BETA_OFF && ICW_BETA_OFF + NR <= ICW_STASH_LD - 1, "stash row layout");

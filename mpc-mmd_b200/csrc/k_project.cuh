@@ -163,15 +163,16 @@ __device__ __forceinline__ void polar_clip(float alpha, float wx, float wy, floa
 }
 
 __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) float sm[];
     float* sP = sm; float* sPd = sP + T_ * NV; float* sPdd = sPd + T_ * NV;
     float* sGx = sPdd + T_ * NV; float* sGy = sGx + 77; float* sKx = sGy + 88; float* sKy = sKx + 154;
-    for (int i = threadIdx.x; i < T_ * NV; i += blockDim.x) { sP[i] = c.P[i]; sPd[i] = c.Pd[i]; sPdd[i] = c.Pdd[i]; }
-    for (int i = threadIdx.x; i < 77; i += blockDim.x) sGx[i] = c.Gx[i];
-    for (int i = threadIdx.x; i < 88; i += blockDim.x) sGy[i] = c.Gy[i];
-    for (int i = threadIdx.x; i < 154; i += blockDim.x) sKx[i] = c.Kx[i];
-    for (int i = threadIdx.x; i < 165; i += blockDim.x) sKy[i] = c.Ky[i];
+    // the 15 KB of constant matrices arrive as ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of ~15 loads and stores per thread
+    __shared__ __align__(8) unsigned long long cbar;
+    static_assert((PROJ_CONST_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (threadIdx.x == 0) mbar_init(&cbar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) bulk_g2s(sm, c.proj_const, PROJ_CONST_FLOATS * 4, &cbar);
+    mbar_wait(&cbar, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * PROJ_WARPS + warp;
     if (g >= a.n_samples) return;                      // whole warp exits together; no block sync below

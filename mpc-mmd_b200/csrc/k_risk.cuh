@@ -203,7 +203,7 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
 enum { ROLL_OPT = 0, ROLL_FLY = 1, ROLL_STAGED = 2 };
 template <int MODE>
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int tid = threadIdx.x, nt = ROLL_THREADS, warp = tid >> 5, lane = tid & 31;
     const int nr = c.nr, np = c.np, n = nr * np, R = ra.R, spb = ra.spb;
@@ -451,7 +451,7 @@ __device__ __forceinline__ long long sort_key64(float x, int idx) {
 
 template <int NR>
 __global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_cem(DCfg c, RollArgs ra) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;

@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t sel_key32(float x) {
 }
 
 __global__ void __launch_bounds__(1024) k_select(DCfg c, SelArgs a) {      // SEL_THREADS threads, SEL_THREADS_BIG for batches above SEL_RANK_MAX
-    extern __shared__ __align__(16) float sm[];    // 64-bit composite keys [B]
+    extern __shared__ __align__(128) float sm[];    // 64-bit composite keys [B]
     const int e = blockIdx.x;
     if (e >= a.n_ep) return;
     const int B = a.B, tid = threadIdx.x, nthr = blockDim.x, n20 = c.n_el_cost, n5 = c.n_el;

@@ -168,8 +168,17 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     d.sigma_clip = cfg->sigma_clip; d.inv_nm = (float)(1.0 / nm); d.m2_inv_nm = (float)(-2.0 * (1.0 / nm)); d.beta_del = (float)(1.0 / nr);
     d.sigma_random = cfg->sigma_random;
 #define UP(dst, src, n) if (upload(h, &d.dst, cfg->src, (n))) { mpcmmd_destroy(h); return -1; }
-    UP(P, P, 1100) UP(Pd, Pdot, 1100) UP(Pdd, Pddot, 1100) UP(Gx, Gx, 77) UP(Gy, Gy, 88) UP(Kx, Kx, 154) UP(Ky, Ky, 165) UP(Wfit, Wfit, (size_t)NV * np)
+    UP(Wfit, Wfit, (size_t)NV * np)
 #undef UP
+    {   // P | Pd | Pdd | Gx | Gy | Kx | Ky in one block (cudaMalloc: 256-byte aligned), the layout k_project's shared memory mirrors
+        const float* src[7] = {cfg->P, cfg->Pdot, cfg->Pddot, cfg->Gx, cfg->Gy, cfg->Kx, cfg->Ky};
+        const int cnt[7] = {1100, 1100, 1100, 77, 88, 154, 165};
+        std::vector<float> blk; blk.reserve(PROJ_CONST_FLOATS);
+        for (int i = 0; i < 7; i++) { if (!src[i]) { mpcmmd_destroy(h); return fail("mpcmmd_create: null matrix pointer in config"); } blk.insert(blk.end(), src[i], src[i] + cnt[i]); }
+        const float* base = nullptr;
+        if ((int)blk.size() != PROJ_CONST_FLOATS || upload(h, &base, blk.data(), blk.size())) { mpcmmd_destroy(h); return -1; }
+        d.proj_const = base; d.P = base; d.Pd = base + 1100; d.Pdd = base + 2200; d.Gx = base + 3300; d.Gy = d.Gx + 77; d.Kx = d.Gy + 88; d.Ky = d.Kx + 154;
+    }
     DWork& w = h->w;
     const size_t EB = (size_t)E * B, n = (size_t)nr * np, ncem = (size_t)(B - d.n_el) * NPAR;
 #define AL(p, cnt) if (dalloc(h, &w.p, (cnt))) { mpcmmd_destroy(h); return -1; }
