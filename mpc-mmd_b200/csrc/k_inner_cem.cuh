@@ -337,6 +337,72 @@ __device__ __forceinline__ void icf_chol(float* __restrict__ C, int ldc, int lan
     __syncwarp();
 }
 
+// Cholesky of the d x d covariance by ONE warp, left-looking by PANELS of four columns: lane r owns row r.  For panel j0 = 4p each lane first
+// accumulates its four entries (r, j0..j0+3) over the finished columns k < j0 -- four independent fma chains per lane that share one load of
+// L[r][k] and one broadcast float4 of L[j0..j0+3][k] (the factor is kept TRANSPOSED: LT[k][q] = L[q][k], so both are conflict-free) -- then the
+// 4 x 4 diagonal block is gathered with ten shuffles and factored REDUNDANTLY by every lane in registers (no exchange inside the panel), and each
+// lane finishes its own four entries with the block's columns.  Entry (r, j) accumulates fma(-L_rk, L_jk, .) for k = 0 .. j-1 ascending, then
+// the pivot's square root / reciprocal scaling: the contract's order, bit for bit the same as the column-by-column versions.  7 sync points
+// and ~1500 executed instructions instead of 26 and ~2400 for d = 26.  In place: LT lives in the upper triangle (and diagonal) of C while the
+// untouched part of C's lower triangle still holds the covariance; each lane zeroes its consumed sub-diagonal entries, which is the zero
+// fill the resampling loops rely on (LT[k][q] = 0 for q < k).
+template <int d>
+__device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc, int lane) {
+    constexpr int NG = (d + 3) / 4;
+    const int r = lane < d ? lane : d - 1;                 // lanes >= d shadow the last row (no stores)
+    float* rowp = C + r * ldc;
+#pragma unroll 1
+    for (int p = 0; p < NG; p++) {
+        const int j0 = 4 * p;
+        float4 av = *reinterpret_cast<const float4*>(rowp + j0);          // a(r, j0..j0+3)
+        float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
+#pragma unroll 2
+        for (int k = 0; k < j0; k++) {
+            const float lr = C[k * ldc + r];                               // LT[k][r] = L[r][k]
+            const float4 lj = *reinterpret_cast<const float4*>(C + k * ldc + j0);   // L[j0..j0+3][k]
+            a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+        }
+        // diagonal block b(u', u), u <= u', from lanes j0 + u'
+        const float b00 = __shfl_sync(FULL, a0, j0);
+        const float b10 = __shfl_sync(FULL, a0, j0 + 1), b11 = __shfl_sync(FULL, a1, j0 + 1);
+        const float b20 = __shfl_sync(FULL, a0, j0 + 2), b21 = __shfl_sync(FULL, a1, j0 + 2), b22 = __shfl_sync(FULL, a2, j0 + 2);
+        const float b30 = __shfl_sync(FULL, a0, j0 + 3), b31 = __shfl_sync(FULL, a1, j0 + 3), b32 = __shfl_sync(FULL, a2, j0 + 3), b33 = __shfl_sync(FULL, a3, j0 + 3);
+        const float d0 = sqrtf(b00), r0 = 1.0f / d0;
+        const float l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
+        const float d1 = sqrtf(fmaf(-l10, l10, b11)), r1 = 1.0f / d1;
+        const float l21 = fmaf(-l20, l10, b21) * r1, l31 = fmaf(-l30, l10, b31) * r1;
+        const float d2 = sqrtf(fmaf(-l21, l21, fmaf(-l20, l20, b22))), r2 = 1.0f / d2;
+        const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b32)) * r2;
+        const float d3 = sqrtf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33)))), r3 = 1.0f / d3;
+        // own row: L[r][j0 + u]; on the diagonal the pivot itself, above it nothing
+        float e0 = a0 * r0;
+        a1 = fmaf(-e0, l10, a1); float e1 = a1 * r1;
+        a2 = fmaf(-e1, l21, fmaf(-e0, l20, a2)); float e2 = a2 * r2;
+        a3 = fmaf(-e2, l32, fmaf(-e1, l31, fmaf(-e0, l30, a3))); float e3 = a3 * r3;
+        if (lane == j0) e0 = d0;
+        if (lane == j0 + 1) e1 = d1;
+        if (lane == j0 + 2) e2 = d2;
+        if (lane == j0 + 3) e3 = d3;
+        if (lane < d) {
+            // consumed covariance entries below the diagonal become the zero fill; then column r of LT rows j0..j0+3 (q = r >= k only)
+            float4 z = av;
+            if (j0 + 0 < lane) z.x = 0.0f;
+            if (j0 + 1 < lane) z.y = 0.0f;
+            if (j0 + 2 < lane) z.z = 0.0f;
+            if (j0 + 3 < lane) z.w = 0.0f;
+            if (lane >= j0) *reinterpret_cast<float4*>(rowp + j0) = z;
+        }
+        __syncwarp();
+        if (lane < d) {
+            if (lane >= j0 + 0) C[(j0 + 0) * ldc + lane] = e0;
+            if (lane >= j0 + 1 && j0 + 1 < d) C[(j0 + 1) * ldc + lane] = e1;
+            if (lane >= j0 + 2 && j0 + 2 < d) C[(j0 + 2) * ldc + lane] = e2;
+            if (lane >= j0 + 3 && j0 + 3 < d) C[(j0 + 3) * ldc + lane] = e3;
+        }
+        __syncwarp();
+    }
+}
+
 // Latency variant (used when the whole launch is a single wave of CTAs, e.g. one episode = 100 chains): +2000 SASS instructions, which costs
 // ~10 % throughput on full grids through the instruction cache (measured 208.6 -> 229.8 ms per 200-episode solve) but shortens the pivot
 // chain (mmd_opt p50 latency at batch 1: 8.87 -> 7.54 ms).
@@ -559,7 +625,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
         // -- Cholesky by warp 0, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j into row j of
         //    LT (LT[j][q] = L[q][j], q >= j; zeros for q < j) and subtracts l_ij * LT[j][q] from A[i][q], j < q <= i.  Entry (i,q)
         //    therefore accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.  Rolled on purpose (instruction cache).
-        if (warp == 0) { if constexpr (LAT) icf_chol_unrolled<d>(C, ldc, lane); else icf_chol<d>(C, ldc, lane); }
+        if (warp == 0) { if constexpr (LAT) icf_chol_unrolled<d>(C, ldc, lane); else icf_chol_panel<d>(C, ldc, lane); }
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
         //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in
