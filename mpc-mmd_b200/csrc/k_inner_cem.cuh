@@ -356,7 +356,7 @@ __device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc, i
         const int j0 = 4 * p;
         float4 av = *reinterpret_cast<const float4*>(rowp + j0);          // a(r, j0..j0+3)
         float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < j0; k++) {
             const float lr = C[k * ldc + r];                               // LT[k][r] = L[r][k]
             const float4 lj = *reinterpret_cast<const float4*>(C + k * ldc + j0);   // L[j0..j0+3][k]
