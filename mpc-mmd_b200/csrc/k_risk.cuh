@@ -584,23 +584,57 @@ __global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_
                 }
             }
         } else {
-            float* rd = sm + L.rd;
+            // -- block-wide Cholesky, left-looking by PANELS of four columns (same scheme as icf_chol_panel of k_inner_cem.cuh, one row per
+            //    thread): four independent fma chains per thread over the finished columns k < j0, the 4 x 4 diagonal block published through
+            //    shared memory and factored redundantly by every thread, the factor kept transposed in the upper triangle (LT[k][q] = L[q][k])
+            //    where the resampling reads it.  2 block barriers per panel (52 for d = 101) instead of 2 per column (202), and no thread walks
+            //    a single dependent chain.  Entry (r, j) still accumulates fma(-L_rk, L_jk, .) for k ascending, then sqrt / reciprocal scaling.
+            float* blk = sm + L.rd;                            // 16 floats: diagonal-block partials b(u', u) at blk[4 u' + u]
+            const int r = tid;
 #pragma unroll 1
-            for (int j = 0; j < d; j++) {          // block-wide Cholesky, column by column; contract order: ascending-k fma chain
-                for (int r = j + tid; r < d; r += nt) {
-                    float acc = C[r * ldc + j];
-                    for (int k = 0; k < j; k++) acc = fmaf(-C[r * ldc + k], C[j * ldc + k], acc);
-                    if (r == j) { const float dd = sqrtf(acc); C[j * ldc + j] = dd; rd[j] = 1.0f / dd; }
-                    else C[r * ldc + j] = acc;                  // provisional, scaled by 1/L[j][j] after the barrier
+            for (int p = 0; p < (d + 3) / 4; p++) {
+                const int j0 = 4 * p;
+                const bool act = r < d && r >= j0;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                if (act) {
+                    const float4 av = *reinterpret_cast<const float4*>(C + r * ldc + j0);
+                    a0 = av.x; a1 = av.y; a2 = av.z; a3 = av.w;
+#pragma unroll 4
+                    for (int k = 0; k < j0; k++) {
+                        const float lr = C[k * ldc + r];
+                        const float4 lj = *reinterpret_cast<const float4*>(C + k * ldc + j0);
+                        a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+                    }
+                    if (r < j0 + 4) { float* b = blk + 4 * (r - j0); b[0] = a0; b[1] = a1; b[2] = a2; b[3] = a3; }
                 }
                 __syncthreads();
-                for (int r = j + 1 + tid; r < d; r += nt) C[r * ldc + j] = C[r * ldc + j] * rd[j];
+                if (act) {
+                    const float b00 = blk[0], b10 = blk[4], b11 = blk[5], b20 = blk[8], b21 = blk[9], b22 = blk[10];
+                    const float b30 = blk[12], b31 = blk[13], b32 = blk[14], b33 = blk[15];
+                    const float d0 = sqrtf(b00), r0 = 1.0f / d0;
+                    const float l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
+                    const float d1 = sqrtf(fmaf(-l10, l10, b11)), r1 = 1.0f / d1;
+                    const float l21 = fmaf(-l20, l10, b21) * r1, l31 = fmaf(-l30, l10, b31) * r1;
+                    const float d2 = sqrtf(fmaf(-l21, l21, fmaf(-l20, l20, b22))), r2 = 1.0f / d2;
+                    const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b32)) * r2;
+                    const float d3 = sqrtf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33)))), r3 = 1.0f / d3;
+                    float e0 = a0 * r0;
+                    a1 = fmaf(-e0, l10, a1); float e1 = a1 * r1;
+                    a2 = fmaf(-e1, l21, fmaf(-e0, l20, a2)); float e2 = a2 * r2;
+                    a3 = fmaf(-e2, l32, fmaf(-e1, l31, fmaf(-e0, l30, a3))); float e3 = a3 * r3;
+                    if (r == j0) e0 = d0;
+                    if (r == j0 + 1) e1 = d1;
+                    if (r == j0 + 2) e2 = d2;
+                    if (r == j0 + 3) e3 = d3;
+                    // column r of LT rows j0..j0+3 (q = r >= k only); the consumed sub-diagonal entries of row r are left as they are:
+                    // the resampling below never reads the lower triangle
+                    if (r >= j0 + 0) C[(j0 + 0) * ldc + r] = e0;
+                    if (r >= j0 + 1 && j0 + 1 < d) C[(j0 + 1) * ldc + r] = e1;
+                    if (r >= j0 + 2 && j0 + 2 < d) C[(j0 + 2) * ldc + r] = e2;
+                    if (r >= j0 + 3 && j0 + 3 < d) C[(j0 + 3) * ldc + r] = e3;
+                }
                 __syncthreads();
             }
-            // -- L transposed into the (unused) upper triangle: C[k][q] = L[q][k] for q > k, so row k of C from column k on is column k of L
-#pragma unroll 1
-            for (int i = tid; i < d * d; i += nt) { const int q = i / d, k = i % d; if (k < q) C[k * ldc + q] = C[q * ldc + k]; }
-            __syncthreads();
             // -- resample  [compute_beta.py:63-66]: task = (new row r, 8 consecutive columns q0..q0+7); acc_u = sum_{k <= q0+u} L[q0+u][k] z[r][k],
             //    k ascending (the contract's chain), with the 8 columns of a step read as two float4 of row k.  Warps take consecutive r for one
             //    column group: the L reads broadcast and the normals (a constant table, [iter][k][row]) are read coalesced from L1/L2.
