@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 __host__ __device__ constexpr int risko_threads(int nr) { return nr * nr + 1 <= 32 ? RISKO_THREADS : RISKO_THREADS_BIG; }
 
 struct OptLayout {          // shared-memory carve-up (in floats); every offset is a multiple of 4 floats (16 B)
-    int F, D, small, red, th, cost, betas, idxs, key64, perm, C, rd, mean, eth, xc, ecost, ebetas, eidxs;
+    int F, D, small, red, th, cost, betas, idxs, key64, perm, C, rd, mean, eth, xc, ecost, ebetas, eidxs, rs;
     int ldc, total;
 };
 __host__ __device__ inline int al4(int x) { return (x + 3) & ~3; }
@@ -343,6 +343,7 @@ __host__ __device__ inline OptLayout opt_layout(int nr, int np, int S, int ne) {
     L.th = q; q += al4(S * d); L.cost = q; q += al4(S); L.betas = q; q += al4(S * nr); L.idxs = q; q += al4(S * nr);
     L.key64 = q; q += al4(2 * S); L.perm = q; q += al4(S); L.C = q; q += al4(d * L.ldc); L.rd = q; q += al4(d); L.mean = q; q += al4(d);
     L.eth = q; q += al4(ne * d); L.xc = q; q += al4(ne * d); L.ecost = q; q += al4(ne); L.ebetas = q; q += al4(ne * nr); L.eidxs = q; q += al4(ne * nr);
+    L.rs = q; if (d > 32) q += al4(S * nr);           // per-(sample, reduced index) kernel row sums of the phased evaluation (large reduced sets)
     L.total = q;
     return L;
 }
@@ -351,9 +352,10 @@ __host__ __device__ inline OptLayout opt_layout(int nr, int np, int S, int ne) {
 // chain's distance table, solve the equality-constrained QP by Cholesky block elimination, return the MMD cost
 // [compute_beta.py:113-129, 70-91].  |theta| is compared through its bit pattern (non-negative floats order like
 // integers and NaN patterns sort last), which is the jnp.argsort order.
+// the three stages of one beta sample; beta_sample = beta_topk -> beta_rowsum (x NR) -> beta_finish.  The generic kernel for large reduced
+// sets runs them as separate block-wide phases (one task per (sample, reduced index) in the exp-heavy middle stage).
 template <int NR>
-__device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
-                                             float* __restrict__ beta_out, int* __restrict__ idx_out) {
+__device__ __forceinline__ void beta_topk(const float* __restrict__ row, int* __restrict__ ti_out) {
     constexpr int nm = NR * NR;
     int tv[NR], ti[NR];
 #pragma unroll
@@ -370,17 +372,22 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restr
             tv[p] = mv ? a1 : a0; tv[p + 1] = mv ? a0 : a1; ti[p] = mv ? b1 : b0; ti[p + 1] = mv ? b0 : b1;
         }
     }
-    const float sigma = row[nm];
+#pragma unroll
+    for (int i = 0; i < NR; i++) ti_out[i] = ti[i];
+}
+// sum_m exp(-(D[m][ti] / sigma)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]; D is symmetric bit for bit
+__device__ __forceinline__ float beta_rowsum(const float* __restrict__ D, int nm, int ti, float sigma) {
     const float rinv = 1.0f / sigma;
-    float rowsum[NR];
-#pragma unroll
-    for (int i = 0; i < NR; i++) rowsum[i] = 0.0f;
-#pragma unroll 1
-    for (int m = 0; m < nm; m++) {                 // D is symmetric bit for bit: read column m (bank-conflict free across threads)
-        const float* Dm = D + m * nm;
-#pragma unroll
-        for (int i = 0; i < NR; i++) rowsum[i] = rowsum[i] + dm::exp_nonpos(-(Dm[ti[i]] * rinv));
-    }
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int m = 0; m < nm; m++) acc = acc + dm::exp_nonpos(-(D[m * nm + ti] * rinv));
+    return acc;
+}
+template <int NR>
+__device__ __forceinline__ float beta_finish(const DCfg& c, const int* __restrict__ ti, float sigma, const float* __restrict__ rowsum,
+                                             const float* __restrict__ D, float* __restrict__ beta_out) {
+    constexpr int nm = NR * NR;
+    const float rinv = 1.0f / sigma;
     float K[NR][NR];                               // ker_red (symmetric bit for bit); diagonal: exp(-(0 * rinv)) = 1
 #pragma unroll
     for (int i = 0; i < NR; i++) {
@@ -436,8 +443,30 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restr
         s2 = fmaf(c.m2_inv_nm * rowsum[i], beta[i], s2);
     }
 #pragma unroll
-    for (int i = 0; i < NR; i++) { beta_out[i] = beta[i]; idx_out[i] = ti[i]; }
+    for (int i = 0; i < NR; i++) beta_out[i] = beta[i];
     return s1 + s2;
+}
+
+template <int NR>
+__device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
+                                             float* __restrict__ beta_out, int* __restrict__ idx_out) {
+    constexpr int nm = NR * NR;
+    int ti[NR];
+    beta_topk<NR>(row, ti);
+    const float sigma = row[nm];
+    const float rinv = 1.0f / sigma;
+    float rowsum[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) rowsum[i] = 0.0f;
+#pragma unroll 1
+    for (int m = 0; m < nm; m++) {                 // D is symmetric bit for bit: read column m (bank-conflict free across threads)
+        const float* Dm = D + m * nm;
+#pragma unroll
+        for (int i = 0; i < NR; i++) rowsum[i] = rowsum[i] + dm::exp_nonpos(-(Dm[ti[i]] * rinv));
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) idx_out[i] = ti[i];
+    return beta_finish<NR>(c, ti, sigma, rowsum, D, beta_out);
 }
 
 // float -> int64 key whose signed order is "ascending float, -0 == +0, NaN last", tie-broken by the index in the low bits
@@ -490,8 +519,26 @@ __global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_
 #pragma unroll 1
     for (int it = 0; it < c.iters_in; it++) {
         // -- evaluate the new samples (all of them in iteration 0; afterwards rows 0..ne-1 are last iteration's elites)
+        if constexpr (SMALL) {
 #pragma unroll 1
-        for (int s = (it == 0 ? 0 : ne) + tid; s < S; s += nt) cost[s] = beta_sample<NR>(c, th + s * d, D, betas + s * NR, idxs + s * NR);
+            for (int s = (it == 0 ? 0 : ne) + tid; s < S; s += nt) cost[s] = beta_sample<NR>(c, th + s * d, D, betas + s * NR, idxs + s * NR);
+        } else {
+            // phased evaluation: (A) top-NR per sample, (B) one task per (sample, reduced index): the nm-term kernel row sum -- 97 % of the
+            // exponentials, spread over all threads instead of one thread per sample --, (C) the (nr+1) KKT solve and the cost per sample
+            const int s0 = (it == 0 ? 0 : ne);
+            float* rs = sm + L.rs;
+#pragma unroll 1
+            for (int s = s0 + tid; s < S; s += nt) beta_topk<NR>(th + s * d, idxs + s * NR);
+            __syncthreads();
+#pragma unroll 1
+            for (int task = tid; task < (S - s0) * NR; task += nt) {
+                const int s = s0 + task / NR, i = task % NR;
+                rs[s * NR + i] = beta_rowsum(D, nm, idxs[s * NR + i], th[s * d + nm]);
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int s = s0 + tid; s < S; s += nt) cost[s] = beta_finish<NR>(c, idxs + s * NR, th[s * d + nm], rs + s * NR, D, betas + s * NR);
+        }
         __syncthreads();
 #pragma unroll 1
         for (int s = tid; s < S; s += nt) key64[s] = sort_key64(cost[s], s);
