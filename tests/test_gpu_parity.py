@@ -430,3 +430,30 @@ def test_full_sweep_is_batch_invariant(mods):
     for k in pick:
         ref = ora.solve("cvar", int(batch["idx_mpc"][k]), init_state, mean, cov, batch["x_obs_traj"][k], batch["y_obs_traj"][k], v_des)
         _eq(out["cx"][k], ref["cx"], f"episode {k} cx vs oracle"); _eq(out["cost_obs"][k], ref["cost_obs"], f"episode {k} cost_obs vs oracle")
+
+
+def test_full_sweep_matches_oracle_episode_by_episode(mods):
+    """BASELINE configs[1] at full size: ALL 200 episodes of the cvar sweep and 12 episodes of the mmd_opt sweep, solved in one batch each,
+    against the oracle episode by episode -- trajectories, costs, and the accepted set that main_mpc.py would write (cost_obs <= threshold)."""
+    cem_impl, O = mods
+    from mpcmmd_b200 import scenes
+    args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
+    big = cem_impl.CEM(*args, variant="static", max_episodes=200)
+    ora = O.OracleCEM(*args, variant="static")
+    O.set_threads(__import__("os").cpu_count() or 1)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    batch = scenes.static_batch(big, list(range(200)))
+    out = big.solve_batch("cvar", **batch)
+    acc_gpu, acc_ref = [], []
+    for k in range(200):
+        ref = ora.solve("cvar", int(batch["idx_mpc"][k]), init_state, mean, cov, batch["x_obs_traj"][k], batch["y_obs_traj"][k], v_des)
+        for f in ("cx", "cy", "cost_obs", "cost_lane"):
+            _eq(out[f][k], ref[f], f"cvar episode {k} {f}")
+        acc_gpu.append(bool(out["cost_obs"][k] <= 1e-5)); acc_ref.append(bool(ref["cost_obs"] <= 1e-5))
+    assert acc_gpu == acc_ref and 100 < sum(acc_gpu) < 200
+    sub = {n: v[:12] for n, v in batch.items()}
+    out = big.solve_batch("mmd_opt", **sub)
+    for k in range(12):
+        ref = ora.solve("mmd_opt", int(sub["idx_mpc"][k]), init_state, mean, cov, sub["x_obs_traj"][k], sub["y_obs_traj"][k], v_des)
+        for f in ("cx", "cy", "cost_obs", "cost_lane", "beta", "sigma", "res_beta"):
+            _eq(out[f][k], ref[f], f"mmd_opt episode {k} {f}")
