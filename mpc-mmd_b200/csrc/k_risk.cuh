@@ -6,9 +6,10 @@
 //   beta_cem.compute_cem (+ compute_mean_cov_beta, compute_beta_reduced)          S/compute_beta.py:93-157, 51-91
 //   kernel_matrix.compute_kernel / compute_mmd (Laplace kernel)                   S/kernel_computation.py:19-87
 //   Costs.compute_f_bar / compute_lane_bar / compute_{mmd,cvar,saa}_{obs,lane}     S/optimizer/costs.py:50-71, 121-234
-// k_rollouts : noisy controls + rollouts for a group of samples; finishes cvar / saa / mmd_random.
-// k_inner_cem: one CTA per sample (mmd_opt: the inner reduced-set CEM, the dominant cost of a solve,
-//              plus the MMD risk of the chosen set), all state in shared memory.
+// k_rollouts<MODE>: noisy controls + rollouts; ROLL_OPT writes the mother samples' ridge-fit features and controls for the inner CEM,
+//              ROLL_FLY / ROLL_STAGED finish cvar / saa / mmd_random (risk folded into the rollout / reduced by a warp per sample).
+// k_inner_cem<NR>: generic reduced-set inner CEM, one CTA per sample with all state in shared memory (num_reduced 6..10, and the
+//              reference for the kernel-variant tests); the production kernel for num_reduced <= 5 is k_inner_cem_fast (k_inner_cem.cuh).
 #pragma once
 #include "common.cuh"
 
@@ -125,11 +126,12 @@ __device__ __noinline__ float cvar_cost(const DCfg& c, const float* v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_rollouts: noisy controls + Euler rollouts for a group of samples per CTA.  cost kinds with num_reduced rollouts
-// (cvar / saa / mmd_random) finish here with their risk functional; mmd_opt writes the num_reduced^2 mother rollouts and
-// their ridge-fit features for k_inner_cem.  Splitting the solve this way keeps each kernel's instruction footprint
-// inside the 32 KB L1.5 instruction cache (v1 of this file, one fused kernel of 13.7k SASS instructions, spent
-// 6.7 issue slots stalled on instruction fetch per instruction issued -- profiles/r01_v2_summary.md).
+// k_rollouts: noisy controls + Euler rollouts, one thread per rollout.  Cost kinds with num_reduced rollouts (cvar / saa / mmd_random) finish
+// here with their risk functional; mmd_opt writes the ridge-fit features of the num_reduced^2 mother rollouts (and the sample's noisy
+// controls) for the inner-CEM kernel -- the rollouts themselves never leave the registers.  The solve is split into small kernels on
+// purpose: v1 of this file, one fused kernel of 13.7k SASS instructions, spent 6.7 issue slots stalled on instruction fetch per instruction
+// issued (profiles/r01_v1_summary.md), and every later measurement confirmed that code size is the first-order cost here
+// (profiles/r01_v9_summary.md).
 #define ROLL_THREADS 128
 struct RollArgs {
     RiskArgs r;

@@ -28,15 +28,6 @@ struct SelArgs {
 #define SEL_THREADS_BIG 1024
 #define SEL_RANK_MAX 1024   // up to this batch size the 64-bit keys are staged in shared memory and ranked by counting
 
-// (risk, res_norm, index) lexicographic "j before i", NaN last in each key
-__device__ __forceinline__ bool sel_before(float rj, float nj, int j, float ri, float ni, int i) {
-    if (dm::lt_nanlast(rj, ri)) return true;
-    if (dm::lt_nanlast(ri, rj)) return false;
-    if (dm::lt_nanlast(nj, ni)) return true;
-    if (dm::lt_nanlast(ni, nj)) return false;
-    return j < i;
-}
-
 // float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order)
 __device__ __forceinline__ uint32_t sel_key32(float x) {
     const float xz = x + 0.0f;
