@@ -61,12 +61,17 @@ __host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
     L.ldc = al4(d);
     int q = 0;
     L.D = q; q += al4(nm * nm);
-    L.th = q; q += al4(S * L.ldt > nm * 2 * NV ? S * L.ldt : nm * 2 * NV);      // new rows; aliased by the mother features while D is built
+    {   // the S - ne resampled rows (iteration 0 reads the constant theta0 table straight from global memory); the region is also borrowed by the
+        // mother features while D is built and by the centered elites xc between the elite gather and the covariance (the rows are dead then)
+        int n = (S - ne) * L.ldt;
+        if (nm * 2 * NV > n) n = nm * 2 * NV;
+        if (ICF_MAX_NE * L.ldc > n) n = ICF_MAX_NE * L.ldc;
+        L.th = q; L.xc = q; q += al4(n);
+    }
     L.cost = q; q += al4(S); L.betas = q; L.idxs = q;      // the per-row beta / packed-index records live in a global scratch (L2): only <= ne of S rows are read back
                                                            // per iteration, and the 2.4 KB they took in shared memory is what separates 9 from 10 chains per SM
-    L.eth = q; q += 2 * al4(ne * L.ldt); L.ecost = q; q += 2 * al4(ne); L.ebetas = q; q += 2 * al4(ne * nr); L.eidxs = q; q += 2 * al4(ne);
+    L.eth = q; q += al4(ne * L.ldt); L.ecost = q; q += 2 * al4(ne); L.ebetas = q; q += 2 * al4(ne * nr); L.eidxs = q; q += 2 * al4(ne);
     L.perm = q; q += al4(ne);
-    L.xc = q; q += ICF_MAX_NE * L.ldc;       // centered elites, row el, 16-byte aligned rows
     L.C = q; q += d * L.ldc;                 // covariance (lower, row-major); overwritten in place by L transposed (LT[k][q] = L[q][k])
     L.mean = q; q += L.ldc;
     L.small = q; q += 64; L.red = q; q += al4(3 * nr * (ICF_THREADS / 32));
@@ -527,7 +532,7 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
 }
 
 template <int NR, bool LAT>
-__global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
@@ -542,9 +547,8 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
     float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = ra.bscratch + (size_t)g * S * (NR + 1); int* idxs = (int*)(betas + S * NR);
     int* perm = (int*)(sm + L.perm); float* xc = sm + L.xc; float* C = sm + L.C; float* LT = C; float* mean = sm + L.mean;
     float* small = sm + L.small;
-    const int eth_sz = al4(ne * ldt), ecost_sz = al4(ne), eb_sz = al4(ne * NR), ei_sz = al4(ne);
-#pragma unroll 1
-    for (int i = tid; i < ICF_MAX_NE * ldc; i += nt) xc[i] = 0.0f;                 // pad columns / rows stay zero
+    float* eth = sm + L.eth;
+    const int ecost_sz = al4(ne), eb_sz = al4(ne * NR), ei_sz = al4(ne);
     // ---- distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
     {
         float* F = th;
@@ -562,9 +566,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
         }
         __syncthreads();
     }
-    // ---- iteration 0 evaluates the S rows of theta0 (a constant table); later iterations the S - ne resampled rows
-#pragma unroll 1
-    for (int i = tid; i < S * d; i += nt) th[(i / d) * ldt + (i % d)] = __ldg(c.theta0 + i);
+    // ---- iteration 0 evaluates the S rows of theta0 (a constant table, read in place from global memory); later iterations the S - ne resampled rows
     // covariance task of this thread: row cr, columns 4*cg .. 4*cg+3 (lower triangle in groups of four; tasks beyond nt wrap)
     int cr = -1, cg = 0, cr2 = -1, cg2 = 0;
     {
@@ -581,34 +583,32 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
     for (int it = 0; it < c.iters_in; it++) {
         const int cur = it & 1, nxt = cur ^ 1;
         const int n_old = it == 0 ? 0 : ne, n_new = S - n_old;
-        float* eth_c = sm + L.eth + cur * eth_sz; float* eth_n = sm + L.eth + nxt * eth_sz;
+        const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;      // where this iteration's new rows live
         float* ecost_c = sm + L.ecost + cur * ecost_sz; float* ecost_n = sm + L.ecost + nxt * ecost_sz;
         float* eb_c = sm + L.ebetas + cur * eb_sz; float* eb_n = sm + L.ebetas + nxt * eb_sz;
         int* ei_c = (int*)(sm + L.eidxs) + cur * ei_sz; int* ei_n = (int*)(sm + L.eidxs) + nxt * ei_sz;
         // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
 #pragma unroll 1
-        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, th + s * ldt, D, betas + s * NR, idxs + s);
+        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
         if (warp == 0) icf_select(lane, S, n_old, ne, ecost_c, cost, perm, ecost_n);
         __syncthreads();
-        // -- gather the elites (rank order), their mean and the centered rows  [compute_beta.py:56-61]
+        // -- gather the elites (rank order), their mean and the centered rows  [compute_beta.py:56-61].  Two phases around a barrier: every
+        //    read of the old elite rows / the new rows happens before any write, so the elites need one buffer and xc can live in the (now
+        //    dead) row region
+        float v[ICF_MAX_NE]; float mu = 0.0f;
         if (tid < d) {
             float s = 0.0f;
-            float v[ICF_MAX_NE];
 #pragma unroll
             for (int el = 0; el < ICF_MAX_NE; el++) {
                 if (el < ne) {
                     const int p = perm[el];
-                    v[el] = p < n_old ? eth_c[p * ldt + tid] : th[(p - n_old) * ldt + tid];
-                    eth_n[el * ldt + tid] = v[el];
+                    v[el] = p < n_old ? eth[p * ldt + tid] : rows[(p - n_old) * rstride + tid];
                     s = s + v[el];
                 }
             }
-            const float mu = s / (float)ne;
-            mean[tid] = mu;
-#pragma unroll
-            for (int el = 0; el < ICF_MAX_NE; el++) if (el < ne) xc[el * ldc + tid] = v[el] - mu;
+            mu = s / (float)ne;
         } else if (tid >= 32) {
 #pragma unroll 1
             for (int i = tid - 32; i < ne * NR; i += nt - 32) {
@@ -616,6 +616,12 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
                 eb_n[i] = p < n_old ? eb_c[p * NR + k] : betas[(p - n_old) * NR + k];
             }
             if (tid - 32 < ne) { const int p = perm[tid - 32]; ei_n[tid - 32] = p < n_old ? ei_c[p] : idxs[p - n_old]; }
+        }
+        __syncthreads();
+        if (tid < d) {
+            mean[tid] = mu;
+#pragma unroll
+            for (int el = 0; el < ICF_MAX_NE; el++) if (el < ne) { eth[el * ldt + tid] = v[el]; xc[el * ldc + tid] = v[el] - mu; }
         }
         __syncthreads();
         // -- jnp.cov (ddof = 1) + 0.05 I, lower triangle, four columns per task  [compute_beta.py:61]
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 10) k_inner_cem_fast(DCfg c, Roll
             if (it == c.iters_in - 1) {                // beta / reduced set of the best sample; sigma from the RESAMPLED array [Q7]
                 for (int i = 0; i < NR; i++) { small[i] = eb_n[i]; ((int*)small)[16 + i] = (ei_n[0] >> (5 * i)) & 31; }
                 const int p0 = perm[0];
-                small[48] = p0 < ne ? eth_n[p0 * ldt + nm] : th[(p0 - ne) * ldt + nm];
+                small[48] = p0 < ne ? eth[p0 * ldt + nm] : th[(p0 - ne) * ldt + nm];
             }
         }
         // the next iteration's first barrier (after the evaluation) orders these reads against later writes of perm / th
