@@ -68,13 +68,14 @@ __host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
         if (ICF_MAX_NE * L.ldc > n) n = ICF_MAX_NE * L.ldc;
         L.th = q; L.xc = q; q += al4(n);
     }
-    L.cost = q; q += al4(S); L.betas = q; L.idxs = q;      // the per-row beta / packed-index records live in a global scratch (L2): only <= ne of S rows are read back
+    L.cost = q; L.betas = q; L.idxs = q;                 // cost: see C below      // the per-row beta / packed-index records live in a global scratch (L2): only <= ne of S rows are read back
                                                            // per iteration, and the 2.4 KB they took in shared memory is what separates 9 from 10 chains per SM
-    L.eth = q; q += al4(ne * L.ldt); L.ecost = q; q += 2 * al4(ne); L.ebetas = q; q += 2 * al4(ne * nr); L.eidxs = q; q += 2 * al4(ne);
+    L.eth = q; q += al4(ne * L.ldt); L.ecost = q; q += al4(ne); L.ebetas = q; q += al4(ne * nr); L.eidxs = q; q += al4(ne);      // single buffers: readers finish before a barrier, writers start after it
     L.perm = q; q += al4(ne);
-    L.C = q; q += d * L.ldc;                 // covariance (lower, row-major); overwritten in place by L transposed (LT[k][q] = L[q][k])
+    L.C = q; L.cost = q; q += d * L.ldc;     // covariance (lower, row-major); overwritten in place by L transposed (LT[k][q] = L[q][k]).  The S sample
+                                             // costs borrow the same region: they live from the evaluation to the selection, C from the covariance to the resampling
     L.mean = q; q += L.ldc;
-    L.small = q; q += 64; L.red = q; q += al4(3 * nr * (ICF_THREADS / 32));
+    L.small = q; q += 52; L.red = q;
     L.total = q;
     return L;
 }
@@ -275,18 +276,18 @@ __device__ __forceinline__ uint32_t sort_key32(float x) {
 }
 
 
-// stable argsort of the S candidate costs, first ne entries, by ONE warp (S <= 128): candidate j < n_old is elite j (cost ecost_c[j]),
+// stable argsort of the S candidate costs, first ne entries, by ONE warp (S <= 128): candidate j < n_old is elite j (cost ecost[j]),
 // else new row j - n_old (cost[j - n_old]).  Each lane sorts its four candidates (j = lane + 32u, stable), then ne rounds of
 // redux.sync min pick the globally smallest (key, index).  Writes perm[0..ne) and the winners' costs.  [compute_beta.py:56]
-__device__ __forceinline__ void icf_select(int lane, int S, int n_old, int ne, const float* __restrict__ ecost_c, const float* __restrict__ cost,
-                                           int* __restrict__ perm, float* __restrict__ ecost_n) {
+// (ecost_n may be the same buffer as ecost: every read of the old elite costs precedes the first write)
+__device__ __forceinline__ void icf_select(int lane, int S, int n_old, int ne, const float* ecost, const float* __restrict__ cost, int* __restrict__ perm, float* ecost_n) {
     uint32_t k0, k1, k2, k3; int j0, j1, j2, j3;
     {
         uint32_t kk[4]; int jj[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = lane + 32 * u;
-            if (j < S) { kk[u] = sort_key32(j < n_old ? ecost_c[j] : cost[j - n_old]); jj[u] = j; }
+            if (j < S) { kk[u] = sort_key32(j < n_old ? ecost[j] : cost[j - n_old]); jj[u] = j; }
             else { kk[u] = 0xffffffffu; jj[u] = 0x7fffffff; }
         }
         // stable local sort (adjacent exchanges only; indices ascend within a lane)
@@ -304,10 +305,10 @@ __device__ __forceinline__ void icf_select(int lane, int S, int n_old, int ne, c
         if ((uint32_t)j0 == wj) { k0 = k1; k1 = k2; k2 = k3; k3 = 0xffffffffu; j0 = j1; j1 = j2; j2 = j3; j3 = 0x7fffffff; }
         if (lane == r) mine = (int)wj;
     }
-    if (lane < ne) {
-        perm[lane] = mine;
-        ecost_n[lane] = mine < n_old ? ecost_c[mine] : cost[mine - n_old];
-    }
+    float won = 0.0f;
+    if (lane < ne) won = mine < n_old ? ecost[mine] : cost[mine - n_old];
+    __syncwarp();                                  // every read of the old elite costs precedes the overwrite (one buffer)
+    if (lane < ne) { perm[lane] = mine; ecost_n[lane] = won; }
 }
 
 // Cholesky of the d x d covariance by ONE warp, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j
@@ -532,7 +533,7 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
 }
 
 template <int NR, bool LAT>
-__global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, Roll
     int* perm = (int*)(sm + L.perm); float* xc = sm + L.xc; float* C = sm + L.C; float* LT = C; float* mean = sm + L.mean;
     float* small = sm + L.small;
     float* eth = sm + L.eth;
-    const int ecost_sz = al4(ne), eb_sz = al4(ne * NR), ei_sz = al4(ne);
+    float* ecost = sm + L.ecost; float* eb = sm + L.ebetas; int* ei = (int*)(sm + L.eidxs);
     // ---- distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
     {
         float* F = th;
@@ -581,23 +582,19 @@ __global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, Roll
     float* resb = a.res_beta + (size_t)g * c.iters_in;
 #pragma unroll 1
     for (int it = 0; it < c.iters_in; it++) {
-        const int cur = it & 1, nxt = cur ^ 1;
         const int n_old = it == 0 ? 0 : ne, n_new = S - n_old;
         const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;      // where this iteration's new rows live
-        float* ecost_c = sm + L.ecost + cur * ecost_sz; float* ecost_n = sm + L.ecost + nxt * ecost_sz;
-        float* eb_c = sm + L.ebetas + cur * eb_sz; float* eb_n = sm + L.ebetas + nxt * eb_sz;
-        int* ei_c = (int*)(sm + L.eidxs) + cur * ei_sz; int* ei_n = (int*)(sm + L.eidxs) + nxt * ei_sz;
         // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
 #pragma unroll 1
         for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
-        if (warp == 0) icf_select(lane, S, n_old, ne, ecost_c, cost, perm, ecost_n);
+        if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);
         __syncthreads();
         // -- gather the elites (rank order), their mean and the centered rows  [compute_beta.py:56-61].  Two phases around a barrier: every
         //    read of the old elite rows / the new rows happens before any write, so the elites need one buffer and xc can live in the (now
         //    dead) row region
-        float v[ICF_MAX_NE]; float mu = 0.0f;
+        float v[ICF_MAX_NE]; float mu = 0.0f, gb = 0.0f; int gi = 0;
         if (tid < d) {
             float s = 0.0f;
 #pragma unroll
@@ -609,19 +606,19 @@ __global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, Roll
                 }
             }
             mu = s / (float)ne;
-        } else if (tid >= 32) {
-#pragma unroll 1
-            for (int i = tid - 32; i < ne * NR; i += nt - 32) {
-                const int p = perm[i / NR], k = i % NR;
-                eb_n[i] = p < n_old ? eb_c[p * NR + k] : betas[(p - n_old) * NR + k];
-            }
-            if (tid - 32 < ne) { const int p = perm[tid - 32]; ei_n[tid - 32] = p < n_old ? ei_c[p] : idxs[p - n_old]; }
+        } else if (tid >= 32 && tid - 32 < ne * NR) {           // one (elite, component) per thread: ne * NR <= 64
+            const int i = tid - 32, p = perm[i / NR], k = i % NR;
+            gb = p < n_old ? eb[p * NR + k] : betas[(p - n_old) * NR + k];
+            if (i < ne) { const int p2 = perm[i]; gi = p2 < n_old ? ei[p2] : idxs[p2 - n_old]; }
         }
         __syncthreads();
         if (tid < d) {
             mean[tid] = mu;
 #pragma unroll
             for (int el = 0; el < ICF_MAX_NE; el++) if (el < ne) { eth[el * ldt + tid] = v[el]; xc[el * ldc + tid] = v[el] - mu; }
+        } else if (tid >= 32 && tid - 32 < ne * NR) {
+            eb[tid - 32] = gb;
+            if (tid - 32 < ne) ei[tid - 32] = gi;
         }
         __syncthreads();
         // -- jnp.cov (ddof = 1) + 0.05 I, lower triangle, four columns per task  [compute_beta.py:61]
@@ -661,9 +658,9 @@ __global__ void __launch_bounds__(ICF_THREADS, 12) k_inner_cem_fast(DCfg c, Roll
         }
         __syncthreads();
         if (tid == 0) {
-            resb[it] = ecost_n[0];
+            resb[it] = ecost[0];
             if (it == c.iters_in - 1) {                // beta / reduced set of the best sample; sigma from the RESAMPLED array [Q7]
-                for (int i = 0; i < NR; i++) { small[i] = eb_n[i]; ((int*)small)[16 + i] = (ei_n[0] >> (5 * i)) & 31; }
+                for (int i = 0; i < NR; i++) { small[i] = eb[i]; ((int*)small)[16 + i] = (ei[0] >> (5 * i)) & 31; }
                 const int p0 = perm[0];
                 small[48] = p0 < ne ? eth[p0 * ldt + nm] : th[(p0 - ne) * ldt + nm];
             }
