@@ -286,9 +286,10 @@ def main():
     avg_launch_s = prof["ms"]["risk"] * 1e-3 / prof["launches"]["risk"]
     peak_tf, sm_count = cem_impl.fp32_peak(local)
     achieved = flops_per_launch / avg_launch_s / 1e12
-    # dram bytes per risk-stage launch from the committed ncu --set full captures (profiles/r01_v9_summary.md): k_inner_cem_fast 46 + 16 MB,
-    # k_rollouts<ROLL_OPT> 19 + 28 MB at the cfg2 shape (k_opt_risk not captured, < 5 MB of controls); null for the other workloads
-    traffic = 109.0e6 if (args.workload == "cfg2") else None
+    # dram bytes per risk-stage launch from the committed ncu --set full captures (profiles/r01_v12_summary.md, r01_v9_summary.md):
+    # k_inner_cem_fast 45 + 12 MB, k_rollouts<ROLL_OPT> 19 + 28 MB at the cfg2 shape (k_opt_risk not captured, < 5 MB of controls); null for the
+    # other workloads
+    traffic = 104.0e6 if (args.workload == "cfg2") else None
     roofline = {"bound": "fp32", "kernel": ("k_rollouts + k_inner_cem_fast<5> + k_opt_risk (mother rollouts, reduced-set inner CEM, MMD risk)" if HEAVY == "mmd_opt"
                                             else "k_rollouts (noisy rollouts + %s risk)" % HEAVY), "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
