@@ -34,11 +34,13 @@ __device__ __forceinline__ float fbar(const DCfg& c, float x, float y, float xo,
     float cost = (-(wc * wc) / c.a2_obs - (ws * ws) / c.b2_obs) + 1.0f;
     return dm::max0_(cost);
 }
-// one step of the Euler bicycle model  [cem_helper.py:380-400]
-__device__ __forceinline__ void bicycle_step(const DCfg& c, float a, float s, float& x, float& y, float& vx, float& vy, float& psi) {
+// one step of the Euler bicycle model  [cem_helper.py:380-400]; `ts` = tan(steer).  The tangent does not depend on the state, so wherever the
+// controls are staged it is taken there, in parallel and once per control element (a mother rollout shares its steering row with
+// num_reduced - 1 others), instead of inside the serial per-step chain.
+__device__ __forceinline__ void bicycle_step(const DCfg& c, float a, float ts, float& x, float& y, float& vx, float& vy, float& psi) {
     float v = sqrtf(vx * vx + vy * vy);
     v = v + a * c.dt;
-    float psidot = (v * dm::tan_(s)) / c.wheel_base;
+    float psidot = (v * ts) / c.wheel_base;
     psi = psi + psidot * c.dt;
     float sp, cp; dm::sincos_(psi, sp, cp);
     vx = v * cp; vy = v * sp;
@@ -60,7 +62,7 @@ __device__ __forceinline__ void rollout_fit(const DCfg& c, const float* a, const
         if (WRITE) { xg[t] = x; yg[t] = y; }
 #pragma unroll
         for (int k = 0; k < NV; k++) { const float w = W[k * np + t]; fx[k] = fmaf(w, x, fx[k]); fy[k] = fmaf(w, y, fy[k]); }
-        bicycle_step(c, a[t], s[t], x, y, vx, vy, psi);
+        bicycle_step(c, a[t], s[t], x, y, vx, vy, psi);          // s = tan(steer), see k_rollouts
     }
 #pragma unroll
     for (int k = 0; k < NV; k++) { feat[k] = fx[k]; feat[NV + k] = fy[k]; }
@@ -141,7 +143,7 @@ struct RollArgs {
     int write_rolls;         // mmd_opt: also write the mother rollouts (only the generic / warp-per-chain inner kernels read them back)
     float *xroll, *yroll;    // [n][R][np]   (mmd_opt, write_rolls only)
     float* feat;             // [n][nm][22]  (mmd_opt only)
-    float* ctrl;             // [n][2][nr*np]  noisy controls of the sample (mmd_opt): k_opt_risk re-rolls the chosen reduced set from them
+    float* ctrl;             // [n][2][nr*np]  noisy acceleration and tan(noisy steering) of the sample (mmd_opt): k_opt_risk re-rolls the chosen reduced set from them
     float* stash;            // [persistent CTAs][S][32]  row stash of k_inner_cem_warp
     int* ridx;               // [n][nr]  reduced set chosen by k_inner_cem_fast, read by k_opt_risk
     float* bscratch;         // [n][S][nr + 1]  per-row beta vectors and packed reduced-set indices of k_inner_cem_fast's current iteration
@@ -192,7 +194,7 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
 #pragma unroll 1
     for (int t = 0; t < np; t++) {
         float at, st;
-        if (FLY) noisy_control(c, A, g, e, row * np + t, t, n, at, st); else { at = a[t]; st = s[t]; }
+        if (FLY) { noisy_control(c, A, g, e, row * np + t, t, n, at, st); st = dm::tan_(st); } else { at = a[t]; st = s[t]; }      // s = tan(steer) when staged
 #pragma unroll 4
         for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
         l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
@@ -221,8 +223,9 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
             float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
-            sm[ls * 2 * n + el] = an; sm[ls * 2 * n + n + el] = sn;
-            ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = sn;
+            const float tn = dm::tan_(sn);                     // the rollouts (and k_opt_risk's re-rolls) only ever need tan(steer)
+            sm[ls * 2 * n + el] = an; sm[ls * 2 * n + n + el] = tn;
+            ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = tn;
         }
         __syncthreads();
         // mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
             float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
-            sm[ls * per + 4 * tail + el] = an; sm[ls * per + 4 * tail + n + el] = sn;
+            sm[ls * per + 4 * tail + el] = an; sm[ls * per + 4 * tail + n + el] = dm::tan_(sn);
         }
         __syncthreads();
     }
