@@ -409,58 +409,6 @@ __device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc, i
     }
 }
 
-// Latency variant (used when the whole launch is a single wave of CTAs, e.g. one episode = 100 chains): +2000 SASS instructions, which costs
-// ~10 % throughput on full grids through the instruction cache (measured 208.6 -> 229.8 ms per 200-episode solve) but shortens the pivot
-// chain (mmd_opt p50 latency at batch 1: 8.87 -> 7.54 ms).
-// Cholesky of the d x d covariance by ONE warp, right-looking: lane i holds row i of the lower triangle IN REGISTERS; step j turns column j
-// into row j of LT (LT[j][q] = L[q][j] for q >= j, zeros for q < j; LT overwrites C in place -- every lane has its row in registers before
-// the first store) and subtracts l_ij * LT[j][q] from a[q], q > j.  Entry (i,q) therefore accumulates fma(-L_ik, L_qk, .) for k ascending:
-// the contract's order.  Fully unrolled: the pivot chain (shfl -> sqrt -> 1/x -> store -> broadcast loads) is the critical path of the
-// whole CTA -- 2 of its 3 warps wait at the barrier behind it (profiles/r01_v8_summary.md: 28 % of all stall samples) -- and the rolled
-// shared-memory version spent 93 warp instructions per pivot against ~35 here.  Entries q > i of a lane hold unused values.
-template <int d>
-__device__ __forceinline__ void icf_chol_unrolled(float* __restrict__ C, int ldc, int lane) {
-    constexpr int NG = (d + 3) / 4;
-    float* LT = C;
-    float a[4 * NG];
-    {
-        const float* rowp = C + (lane < d ? lane : d - 1) * ldc;
-#pragma unroll
-        for (int g4 = 0; g4 < NG; g4++) {
-            const float4 v = *reinterpret_cast<const float4*>(rowp + 4 * g4);
-            a[4 * g4] = v.x; a[4 * g4 + 1] = v.y; a[4 * g4 + 2] = v.z; a[4 * g4 + 3] = v.w;
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < d; j++) {
-        const float ajj = __shfl_sync(FULL, a[j], j);
-        const float dd = sqrtf(ajj);
-        const float rdj = 1.0f / dd;
-        const float lij = lane == j ? dd : a[j] * rdj;
-        if (lane < d) LT[j * ldc + lane] = lane < j ? 0.0f : lij;
-        if (j + 1 < d) {
-            __syncwarp();
-            const pk::f2 nl = pk::dup(-lij);
-            const float* lrow = LT + j * ldc;
-#pragma unroll
-            for (int g4 = (j + 1) / 4; g4 < NG; g4++) {
-                const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * g4);
-                // columns q <= j of the first group are final already (never read again): only q > j is updated
-                if (4 * g4 + 1 > j) {
-                    if (4 * g4 > j) pk::unpack(pk::fma2(nl, pk::pack(l.x, l.y), pk::pack(a[4 * g4], a[4 * g4 + 1])), a[4 * g4], a[4 * g4 + 1]);
-                    else a[4 * g4 + 1] = fmaf(-lij, l.y, a[4 * g4 + 1]);
-                }
-                if (4 * g4 + 3 > j) {
-                    if (4 * g4 + 2 > j) pk::unpack(pk::fma2(nl, pk::pack(l.z, l.w), pk::pack(a[4 * g4 + 2], a[4 * g4 + 3])), a[4 * g4 + 2], a[4 * g4 + 3]);
-                    else a[4 * g4 + 3] = fmaf(-lij, l.w, a[4 * g4 + 3]);
-                }
-            }
-        }
-    }
-    __syncwarp();
-}
-
 // one covariance task: C[r][4*q4 .. 4*q4+3] = (sum_el xc[el][r] * xc[el][q]) / (ne - 1) (+ 0.05 on the diagonal), el ascending  [compute_beta.py:61]
 __device__ __forceinline__ void icf_cov_task(const float* __restrict__ xc, float* __restrict__ C, int ldc, int ne, int r, int q4) {
     const float nm1 = (float)(ne - 1);
@@ -532,6 +480,8 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
     }
 }
 
+// LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): same code with a 96-register budget instead of the
+// 56 registers that let 12 chains share an SM (mmd_opt p50 at batch 1: 8.3 -> 7.6 ms)
 template <int NR, bool LAT>
 __global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
@@ -625,10 +575,8 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DC
         if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
         if (cr2 >= 0) icf_cov_task(xc, C, ldc, ne, cr2, cg2);
         __syncthreads();
-        // -- Cholesky by warp 0, right-looking, in place: lane i owns row i of the lower triangle; step j turns column j into row j of
-        //    LT (LT[j][q] = L[q][j], q >= j; zeros for q < j) and subtracts l_ij * LT[j][q] from A[i][q], j < q <= i.  Entry (i,q)
-        //    therefore accumulates fma(-L_ik, L_qk, .) for k ascending: the contract's order.  Rolled on purpose (instruction cache).
-        if (warp == 0) { if constexpr (LAT) icf_chol_unrolled<d>(C, ldc, lane); else icf_chol_panel<d>(C, ldc, lane); }
+        // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel)
+        if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
         //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in

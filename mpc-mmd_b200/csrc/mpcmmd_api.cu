@@ -327,7 +327,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         // default: one 3-warp CTA per chain (k_inner_cem_fast).  The warp-per-chain persistent kernel is kept as an opt-in
         // (MPCMMD_INNER_CEM=warp): measured 233 ms vs 209 ms per 200-episode mmd_opt solve on B200 (profiles/r01_v7_summary.md) --
         // 19 independent instruction streams per SM thrash the 32 KB instruction cache.
-        // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the unrolled-Cholesky build
+        // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the build with the 96-register budget
         if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 9 * h->sm_count ? INNER_CTA_LAT : INNER_CTA);
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
         f = inner_cem_kernel(d, kind);
