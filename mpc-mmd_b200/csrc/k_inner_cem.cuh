@@ -480,10 +480,29 @@ __device__ __forceinline__ void icf_mvn_row_unrolled(const float* __restrict__ L
     }
 }
 
-// LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): same code with a 96-register budget instead of the
-// 56 registers that let 12 chains share an SM (mmd_opt p50 at batch 1: 8.3 -> 7.6 ms)
+// the same row with the d normals already in registers (latency build: they are fetched before the one-warp Cholesky, whose duration hides
+// their L2 latency; with one chain per SM nothing else would)
+template <int d>
+__device__ __forceinline__ void icf_mvn_row_regs(const float* __restrict__ LT, int ldc, const float (&z)[d], pk::f2 (&acc)[2 * ((d + 3) / 4)]) {
+    constexpr int NG = (d + 3) / 4;
+#pragma unroll
+    for (int p = 0; p < 2 * NG; p++) acc[p] = pk::dup(0.0f);
+#pragma unroll
+    for (int k = 0; k < d; k++) {
+        const pk::f2 z2 = pk::dup(z[k]);
+#pragma unroll
+        for (int g4 = k / 4; g4 < NG; g4++) {
+            const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+            acc[2 * g4] = pk::fma2(pk::pack(l.x, l.y), z2, acc[2 * g4]);
+            acc[2 * g4 + 1] = pk::fma2(pk::pack(l.z, l.w), z2, acc[2 * g4 + 1]);
+        }
+    }
+}
+
+// LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): no register cap (156 instead of the 56 registers
+// that let 12 chains share an SM) and the resampling normals prefetched behind the Cholesky (mmd_opt p50 at batch 1: 8.3 -> 7.4 ms)
 template <int NR, bool LAT>
-__global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
+__global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
@@ -575,6 +594,16 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DC
         if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
         if (cr2 >= 0) icf_cov_task(xc, C, ldc, ne, cr2, cg2);
         __syncthreads();
+        // latency build: this thread's d normals of the coming resampling are requested now and arrive while warp 0 factors
+        float zpre[LAT ? d : 1];
+        const bool pre = LAT && (S - ne) <= nt;
+        if constexpr (LAT) {
+            if (pre && tid < S - ne) {
+                const float* zp = c.zb_iterT + (size_t)it * d * (S - ne) + tid;
+#pragma unroll
+                for (int k = 0; k < d; k++) zpre[k] = __ldg(zp + k * (S - ne));
+            }
+        }
         // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel)
         if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
         __syncthreads();
@@ -588,7 +617,8 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 6 : 12) k_inner_cem_fast(DC
 #pragma unroll 1
             for (int r = tid; r < nrow; r += nt) {
                 pk::f2 acc[2 * NG];
-                icf_mvn_row_unrolled<d>(LT, ldc, zT, nrow, r, acc);
+                if constexpr (LAT) { if (pre) icf_mvn_row_regs<d>(LT, ldc, zpre, acc); else icf_mvn_row_unrolled<d>(LT, ldc, zT, nrow, r, acc); }
+                else icf_mvn_row_unrolled<d>(LT, ldc, zT, nrow, r, acc);
                 float* dst = th + r * ldt;
 #pragma unroll
                 for (int p = 0; p < NPAIR; p++) {
