@@ -22,6 +22,7 @@ struct DCfg {
     float sigma_clip, inv_nm, m2_inv_nm, beta_del, sigma_random;
     const float *P, *Pd, *Pdd, *Gx, *Gy, *Kx, *Ky, *Wfit;   // device copies of the host constants
     const float* proj_const;                                 // P | Pd | Pdd | Gx | Gy | Kx | Ky as ONE 16-byte-aligned block (bulk-copied into shared memory by k_project)
+    const float* proj_tc_const;                              // tf32 (hi, lo) images of P / Pd / Pdd + Gx | Gy | Kx | Ky for k_project_tc
     const float *z_init, *theta0, *zb_iter;                  // constant normal tables (generated at create)
     const float *theta0T;                                    // theta0 transposed to [column][row]
     const float *zb_iterT;                                   // zb_iter transposed to [iter][column][row] for coalesced row-per-thread reads

@@ -141,6 +141,7 @@ struct ProjArgs {           // one batch of samples; sample g = e * B + b uses p
     float *cx, *cy;         // [n][11]
     float *res_norm, *cost_base;   // [n]
     float *acc, *steer;     // [n][100]
+    int dbg;                // k_project_tc only: 1 / 2 = dump the pass-1 products instead of the results (tools/proj_tc_probe.py)
 };
 
 __device__ __forceinline__ float unwrap_corr(float dd) {     // jnp.unwrap phase correction for one difference

@@ -1,0 +1,424 @@
+// k_project_tc.cuh -- tensor-core variant of the projection kernel (opt-in: MPCMMD_PROJ=tc).
+//
+// Same stage as k_project (Helper.compute_x_guess, Projection.compute_projection, Helper.compute_controls and the
+// risk-independent cost terms; reference S/optimizer/cem_helper.py:169-230, :540-551, :232-262, S/optimizer/projection.py:276-323),
+// but the matrix products run on the 5th-generation tensor cores:
+//   * a CTA owns 128 samples; sample r is TMEM lane r, so `tcgen05.ld 32x32b` hands thread r its own row of every product;
+//   * "expansion" products  [128 samples x 16 coefficients] x [16 x 32 knots]  (guess derivatives, projected trajectories):
+//     A = the coefficients, written K-major into shared memory by the owning thread, B = the Bernstein images P / Pdot / Pddot;
+//   * "reduction" products  [128 samples x 8 knots] x [8 x 16 coefficients]  (P^T r for the multiplier and linear-cost updates):
+//     A = residuals / clipped targets of 8 knots, B = a transposed copy of the image (an MN-major descriptor on the first copy
+//     returned zeros for kind::tf32 with SWIZZLE_NONE on B200, measured; both operands are therefore K-major);
+//   * every product is 4 x kind::tf32 MMAs on an error-free round-to-nearest split x = hi + lo of both operands
+//     (lo*lo, lo*hi, hi*lo, hi*hi, smallest first; fp32 accumulation in TMEM), i.e. ~2^-22 relative per product.
+// The element-wise work between the products (atan2 / unwrap / polar clip / lane slacks / controls / cost norms) stays on the
+// CUDA cores with one thread per sample; unwrap and all finite differences are sequential carries in registers.
+// This variant does NOT reproduce the ascending fma chains of the arithmetic contract: it is tested against the oracle at the
+// tolerance north_star states (1e-4), not bit for bit, and is therefore not the default path.
+#pragma once
+#include "k_project.cuh"
+
+namespace ptc {
+constexpr int THREADS = 128;
+constexpr int NROW = 112;                                  // knots padded to 7 x 16
+constexpr uint32_t KSTR = NROW * 16;                       // 1792: bytes between the 16-byte coefficient chunks of an image
+constexpr uint32_t IMG = 4 * KSTR;                         // 7168: one [4 chunks][112 knots][4 coefficients] tf32 image
+constexpr uint32_t RSTR = 16 * 16;                         // 256: bytes between the 4-knot chunks of a transposed image
+constexpr uint32_t RIMG = 26 * RSTR;                       // 6656: one [26 chunks][16 coefficients][4 knots] tf32 image (knots padded to 104)
+constexpr uint32_t OFF_R = 6 * IMG;                        // P_hi P_lo Pd_hi Pd_lo Pdd_hi Pdd_lo, then the same six transposed
+constexpr uint32_t B_BYTES = 6 * IMG + 6 * RIMG;
+constexpr int SMALL = 77 + 88 + 154 + 165;                 // Gx Gy Kx Ky
+constexpr uint32_t CONST_BYTES = B_BYTES + SMALL * 4;      // 84880
+constexpr uint32_t MAT = 4096;                             // one [2 chunks][128 rows][4] part of an A operand (8 knots)
+constexpr uint32_t ABUF = 10 * MAT;                        // 5 matrices x (hi, lo)
+constexpr uint32_t OFF_A = (CONST_BYTES + 127) / 128 * 128;
+constexpr uint32_t SMEM_BYTES = OFF_A + ABUF + 64;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t COL_UW = 160;                           // columns 0..159: five 32-knot blocks; 160..223: four 16-column reductions
+static_assert(CONST_BYTES % 16 == 0, "bulk copy size");
+
+__host__ __device__ constexpr uint32_t idesc(int n, int b_mn) {      // kind::tf32, fp32 accumulate, M = 128, A K-major
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t sdesc(uint32_t addr, uint32_t lbo, uint32_t sbo) {   // SWIZZLE_NONE shared-memory matrix descriptor
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d), "l"(ad), "l"(bd), "r"(id), "r"(accumulate) : "memory");
+}
+// D (+)= (A_hi + A_lo) (B_hi + B_lo), one K = 8 step
+__device__ __forceinline__ void mma4(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo,
+                                     uint32_t id, bool first) {
+    const uint64_t ah = sdesc(a_hi, 2048, 128), al = sdesc(a_lo, 2048, 128);
+    const uint64_t bh = sdesc(b_hi, b_lbo, b_sbo), bl = sdesc(b_lo, b_lbo, b_sbo);
+    mma(d, al, bl, id, first ? 0u : 1u);
+    mma(d, al, bh, id, 1u);
+    mma(d, ah, bl, id, 1u);
+    mma(d, ah, bh, id, 1u);
+}
+__device__ __forceinline__ void commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    __syncwarp();                                                     // .sync.aligned: the warp must be converged (thread 0 issues MMAs on its own)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// error-free split into two tf32 values (round to nearest): x = hi + lo up to 2^-22 |x|
+__device__ __forceinline__ void split(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    const float d = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(d));
+    lo = __uint_as_float(l);
+}
+// 8 knots of one A matrix: slot m of the buffer, (hi, lo) parts, chunk q at q*2048 + row*16
+__device__ __forceinline__ void put8(unsigned char* abuf, int m, int row, const float (&v)[8]) {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) split(v[i], h[i], l[i]);
+    unsigned char* p = abuf + (2 * m) * MAT + row * 16;
+    *reinterpret_cast<float4*>(p) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(p + 2048) = make_float4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<float4*>(p + MAT) = make_float4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4*>(p + MAT + 2048) = make_float4(l[4], l[5], l[6], l[7]);
+}
+// the 2 x 11 coefficients of a sample as the K = 16 operand of the expansion products: x_hi | x_lo | y_hi | y_lo, 8 KB each
+__device__ __forceinline__ void put_coef(unsigned char* abuf, int row, const float (&cf)[22]) {
+#pragma unroll
+    for (int ax = 0; ax < 2; ax++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int j = 4 * q + i;
+                if (j < NV) split(cf[ax * NV + j], h[i], l[i]); else { h[i] = 0.0f; l[i] = 0.0f; }
+            }
+            unsigned char* p = abuf + ax * 16384 + q * 2048 + row * 16;
+            *reinterpret_cast<float4*>(p) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(p + 8192) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+    }
+}
+// expansion products of one knot block: D[q] = coef(axis) x image^T for q = xd, yd, xdd, ydd (, y)
+__device__ __forceinline__ void issue_expand(uint32_t tmem, uint32_t sb, uint32_t ab, int kb, int n, int nq) {
+    const uint32_t id = idesc(n, 0);
+    for (int q = 0; q < nq; q++) {
+        const uint32_t img = sb + (q < 2 ? 2u : q < 4 ? 4u : 0u) * IMG + (uint32_t)kb * 16;   // Pd, Pdd, P (hi; lo = +IMG)
+        const uint32_t ax = ab + ((q == 1 || q == 3 || q == 4) ? 16384u : 0u);
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            mma4(tmem + q * 32, ax + s * 4096, ax + 8192 + s * 4096, img + s * 2 * KSTR, img + IMG + s * 2 * KSTR, KSTR, 128, id, s == 0);
+    }
+}
+// reduction product of one 8-knot chunk: D[acc] (+)= A(slot m) x transposed image[0..15][t0 .. t0+7]
+__device__ __forceinline__ void issue_reduce(uint32_t tmem, uint32_t sb, uint32_t ab, int m, int img_idx, int t0, int acc, bool first) {
+    const uint32_t img = sb + OFF_R + 2u * img_idx * RIMG + (uint32_t)(t0 >> 2) * RSTR;
+    mma4(tmem + COL_UW + acc * 16, ab + 2 * m * MAT, ab + (2 * m + 1) * MAT, img, img + RIMG, RSTR, 128, idesc(16, 0), first);
+}
+__device__ __forceinline__ float sq(float x) { return x * x; }
+}  // namespace ptc
+
+__global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs a) {
+    using namespace ptc;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const uint32_t sb = smem_u32(smraw);
+    const float* sGx = reinterpret_cast<const float*>(smraw + B_BYTES);
+    const float* sGy = sGx + 77; const float* sKx = sGy + 88; const float* sKy = sKx + 154;
+    unsigned char* abuf = smraw + OFF_A;
+    const uint32_t ab = sb + OFF_A;
+    unsigned long long* bar_c = reinterpret_cast<unsigned long long*>(smraw + OFF_A + ABUF);
+    unsigned long long* bar_m = bar_c + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_c + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(bar_c, 1); mbar_init(bar_m, 1); }
+    __syncthreads();
+    if (tid == 0) bulk_g2s(smraw, c.proj_tc_const, CONST_BYTES, bar_c);
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);         // this warp's 32 TMEM lanes
+    mbar_wait(bar_c, 0);
+
+    const int g0 = blockIdx.x * THREADS + tid;
+    const bool live0 = g0 < a.n_samples;
+    const int g = live0 ? g0 : a.n_samples - 1;                         // idle rows shadow the last sample and store nothing
+    const int e = g / a.B;
+    const float* bqx = a.beq_x + e * 3; const float* bqy = a.beq_y + e * 4;
+    uint32_t par = 0; bool pending = false;
+#define PTC_WAIT() do { if (pending) { mbar_wait(bar_m, par); par ^= 1u; pending = false; } } while (0)
+#define PTC_PUBLISH() do { fence_async_smem(); fence_before(); __syncthreads(); } while (0)
+
+    // ---- x_guess (same fma chains as k_project)  [cem_helper.py:169-230]
+    float cf[22];
+    {
+        float in_x[7], in_y[8];
+        const float4 p0 = *reinterpret_cast<const float4*>(a.params + (size_t)g * NPAR), p1 = *reinterpret_cast<const float4*>(a.params + (size_t)g * NPAR + 4);
+        in_x[0] = p0.x; in_x[1] = p0.y; in_x[2] = p0.z; in_x[3] = p0.w; in_x[4] = bqx[0]; in_x[5] = bqx[1]; in_x[6] = bqx[2];
+        in_y[0] = p1.x; in_y[1] = p1.y; in_y[2] = p1.z; in_y[3] = p1.w; in_y[4] = bqy[0]; in_y[5] = bqy[1]; in_y[6] = bqy[2]; in_y[7] = bqy[3];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 7; k++) s = fmaf(sGx[j * 7 + k], in_x[k], s);
+            cf[j] = s;
+            s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s = fmaf(sGy[j * 8 + k], in_y[k], s);
+            cf[NV + j] = s;
+        }
+    }
+    const float* slr = a.s_lane + (size_t)g * 2 * NL;
+
+    // ---- pass 1: guess derivatives -> unwrap -> polar clip -> P^T r, P^T b  [projection.py:73-131, 158-166]
+    {
+        float prev_v = 0.0f, cum_v = 0.0f, prev_a = 0.0f, cum_a = 0.0f;
+        for (int kb = 0; kb < NROW; kb += 32) {
+            const int n = kb < 96 ? 32 : 16, nsc = kb < 96 ? 4 : 1;
+            PTC_WAIT();
+            put_coef(abuf, tid, cf);
+            PTC_PUBLISH();
+            if (tid == 0) { fence_after(); issue_expand(tmem, sb, ab, kb, n, 4); commit(bar_m); }
+            pending = true;
+            PTC_WAIT();
+            fence_after();
+            for (int sc = 0; sc < nsc; sc++) {
+                const int t0 = kb + 8 * sc;
+                float gx[8], gy[8], r_x[8], b_x[8], r_y[8], b_y[8], dl[8];
+                tld8(tl + 0 * 32 + 8 * sc, gx); tld8(tl + 1 * 32 + 8 * sc, gy);
+                tld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int t = t0 + i;
+                    const float raw = dm::atan2_(gy[i], gx[i]);
+                    if (t >= 1) cum_v = cum_v + unwrap_corr(raw - prev_v);
+                    prev_v = raw;
+                    float bx, by;
+                    polar_clip(t >= 1 ? raw + cum_v : raw, gx[i], gy[i], c.v_min, c.v_max, bx, by);
+                    const bool ok = t < T_;
+                    r_x[i] = ok ? gx[i] - bx : 0.0f; b_x[i] = ok ? bx : 0.0f;
+                    r_y[i] = ok ? gy[i] - by : 0.0f; b_y[i] = ok ? by : 0.0f;
+                    dl[i] = (t >= 1 && ok) ? (c.b_lane_ub - __ldg(slr + t - 1)) - (c.b_lane_lb - __ldg(slr + NL + t - 1)) : 0.0f;
+                    if ((a.dbg & 3) == 1 && live0 && ok) { a.acc[(size_t)g * T_ + t] = gx[i]; a.steer[(size_t)g * T_ + t] = gy[i]; }
+                }
+                PTC_WAIT();
+                put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y); put8(abuf, 4, tid, dl);
+                PTC_PUBLISH();
+                if (tid == 0) {
+                    fence_after();
+                    const bool first = t0 == 0;
+                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
+                    issue_reduce(tmem, sb, ab, 1, 1, t0, 1, first);     // Wx  = Pd^T b_vx
+                    issue_reduce(tmem, sb, ab, 2, 1, t0, 2, first);     // Uy  = Pd^T r_vy
+                    issue_reduce(tmem, sb, ab, 3, 1, t0, 3, first);     // Wy  = Pd^T b_vy
+                    issue_reduce(tmem, sb, ab, 4, 0, t0, 3, false);     // Wy += P^T (LA_ub - LA_lb)
+                    commit(bar_m);
+                }
+                pending = true;
+                tld8(tl + 2 * 32 + 8 * sc, gx); tld8(tl + 3 * 32 + 8 * sc, gy);
+                tld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int t = t0 + i;
+                    const float raw = dm::atan2_(gy[i], gx[i]);
+                    if (t >= 1) cum_a = cum_a + unwrap_corr(raw - prev_a);
+                    prev_a = raw;
+                    float bx, by;
+                    polar_clip(t >= 1 ? raw + cum_a : raw, gx[i], gy[i], 0.0f, c.a_max, bx, by);
+                    const bool ok = t < T_;
+                    r_x[i] = ok ? gx[i] - bx : 0.0f; b_x[i] = ok ? bx : 0.0f;
+                    r_y[i] = ok ? gy[i] - by : 0.0f; b_y[i] = ok ? by : 0.0f;
+                    if ((a.dbg & 3) == 2 && live0 && ok) { a.acc[(size_t)g * T_ + t] = gx[i]; a.steer[(size_t)g * T_ + t] = gy[i]; }
+                }
+                PTC_WAIT();
+                put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y);
+                PTC_PUBLISH();
+                if (tid == 0) {
+                    fence_after();
+                    issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
+                    issue_reduce(tmem, sb, ab, 1, 2, t0, 1, false);     // Wx += Pdd^T b_ax
+                    issue_reduce(tmem, sb, ab, 2, 2, t0, 2, false);     // Uy += Pdd^T r_ay
+                    issue_reduce(tmem, sb, ab, 3, 2, t0, 3, false);     // Wy += Pdd^T b_ay
+                    commit(bar_m);
+                }
+                pending = true;
+            }
+        }
+    }
+    PTC_WAIT();
+    fence_after();
+
+    // ---- multiplier update, linear cost, KKT solve  [projection.py:115-119, 158-171]
+    {
+        float ux[8], ux2[8], wx[8], wx2[8], uy[8], uy2[8], wy[8], wy2[8];
+        tld8(tl + COL_UW + 0, ux); tld8(tl + COL_UW + 8, ux2); tld8(tl + COL_UW + 16, wx); tld8(tl + COL_UW + 24, wx2);
+        tld8(tl + COL_UW + 32, uy); tld8(tl + COL_UW + 40, uy2); tld8(tl + COL_UW + 48, wy); tld8(tl + COL_UW + 56, wy2);
+        tld_wait();
+        float rhs_x[14], rhs_y[15];
+        float* lxg = a.lam_x + (size_t)g * NV; float* lyg = a.lam_y + (size_t)g * NV;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const float u_x = j < 8 ? ux[j] : ux2[j - 8], w_x = j < 8 ? wx[j] : wx2[j - 8];
+            const float u_y = j < 8 ? uy[j] : uy2[j - 8], w_y = j < 8 ? wy[j] : wy2[j - 8];
+            const float lx = lxg[j] - u_x, ly = lyg[j] - u_y;
+            rhs_x[j] = (lx + cf[j]) + w_x;
+            rhs_y[j] = (ly + cf[NV + j]) + w_y;
+            if (live0) { lxg[j] = a.dbg ? u_x : lx; lyg[j] = a.dbg ? u_y : ly; }
+            if (a.dbg && live0) { a.cx[(size_t)g * NV + j] = w_x; a.cy[(size_t)g * NV + j] = w_y; }
+        }
+        rhs_x[11] = bqx[0]; rhs_x[12] = bqx[1]; rhs_x[13] = bqx[2];
+        rhs_y[11] = bqy[0]; rhs_y[12] = bqy[1]; rhs_y[13] = bqy[2]; rhs_y[14] = bqy[3];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 14; k++) s = fmaf(sKx[j * 14 + k], rhs_x[k], s);
+            cf[j] = s;
+            s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 15; k++) s = fmaf(sKy[j * 15 + k], rhs_y[k], s);
+            cf[NV + j] = s;
+        }
+        if (live0 && !a.dbg) {
+#pragma unroll
+            for (int j = 0; j < NV; j++) { a.cx[(size_t)g * NV + j] = cf[j]; a.cy[(size_t)g * NV + j] = cf[NV + j]; }
+        }
+    }
+
+    const bool live = live0 && !a.dbg;
+    // ---- pass 2: projected trajectories -> lane slacks, residuals, P^T r, controls, cost terms  [projection.py:173-272, cem_helper.py:540-551, :232-262]
+    float q_acc = 0.0f, q_vel = 0.0f, q_lane = 0.0f;                       // squared residual norms
+    float q_v = 0.0f, q_s = 0.0f, q_sv = 0.0f, q_sa = 0.0f, q_p1 = 0.0f, q_p2 = 0.0f, q_ydd = 0.0f, q_xdd = 0.0f;
+    {
+        const float vdes = a.v_des[e];
+        float v_prev = 0.0f, st_prev = 0.0f, sv_prev = 0.0f;
+        float* slw = a.s_lane + (size_t)g * 2 * NL;
+        float* accg = a.acc + (size_t)g * T_; float* steerg = a.steer + (size_t)g * T_;
+        for (int kb = 0; kb < NROW; kb += 32) {
+            const int n = kb < 96 ? 32 : 16, nsc = kb < 96 ? 4 : 1;
+            PTC_WAIT();
+            put_coef(abuf, tid, cf);
+            PTC_PUBLISH();
+            if (tid == 0) { fence_after(); issue_expand(tmem, sb, ab, kb, n, 5); commit(bar_m); }
+            pending = true;
+            PTC_WAIT();
+            fence_after();
+            for (int sc = 0; sc < nsc; sc++) {
+                const int t0 = kb + 8 * sc;
+                float xd[8], yd[8], xdd[8], ydd[8], yy[8];
+                tld8(tl + 0 * 32 + 8 * sc, xd); tld8(tl + 1 * 32 + 8 * sc, yd); tld8(tl + 2 * 32 + 8 * sc, xdd); tld8(tl + 3 * 32 + 8 * sc, ydd);
+                tld8(tl + 4 * 32 + 8 * sc, yy);
+                tld_wait();
+                float rvx[8], rvy[8], rax[8], ray[8], dlb[8], st8[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int t = t0 + i;
+                    const bool ok = t < T_;
+                    // residuals of the re-projected point  [projection.py:217-255]
+                    float bvx, bvy, bax, bay;
+                    polar_clip(dm::atan2_(yd[i], xd[i]), xd[i], yd[i], c.v_min, c.v_max, bvx, bvy);
+                    polar_clip(dm::atan2_(ydd[i], xdd[i]), xdd[i], ydd[i], 0.0f, c.a_max, bax, bay);
+                    rvx[i] = ok ? xd[i] - bvx : 0.0f; rvy[i] = ok ? yd[i] - bvy : 0.0f;
+                    rax[i] = ok ? xdd[i] - bax : 0.0f; ray[i] = ok ? ydd[i] - bay : 0.0f;
+                    q_vel = fmaf(rvx[i], rvx[i], q_vel); q_vel = fmaf(rvy[i], rvy[i], q_vel);
+                    q_acc = fmaf(rax[i], rax[i], q_acc); q_acc = fmaf(ray[i], ray[i], q_acc);
+                    // lane slacks and residuals at knot t (row t-1 of A_lane_bound)  [projection.py:182-183]
+                    float d = 0.0f;
+                    if (t >= 1 && ok) {
+                        const float Ay = yy[i];
+                        const float s1 = dm::max0_(-Ay + c.b_lane_ub), r1 = (Ay - c.b_lane_ub) + s1;
+                        const float s2 = dm::max0_(Ay + c.b_lane_lb), r2 = (-Ay - c.b_lane_lb) + s2;
+                        if (live) { slw[t - 1] = s1; slw[NL + t - 1] = s2; }
+                        q_lane = fmaf(r1, r1, q_lane); q_lane = fmaf(r2, r2, q_lane);
+                        d = r1 - r2;
+                    }
+                    dlb[i] = d;
+                    // controls and cost terms  [cem_helper.py:540-551, :232-262]
+                    const float s2v = xd[i] * xd[i] + yd[i] * yd[i];
+                    const float v = sqrtf(s2v);
+                    const float curv = (ydd[i] * xd[i] - yd[i] * xdd[i]) / (s2v * sqrtf(s2v));
+                    const float st = dm::atan_(curv * c.wheel_base);
+                    st8[i] = st;
+                    if (ok) {
+                        if (t >= 1) {
+                            if (live) accg[t - 1] = (v - v_prev) / c.dt;
+                            const float sv = st - st_prev;
+                            q_sv = fmaf(sv, sv, q_sv);
+                            q_p2 = fmaf(sq(dm::max0_(fabsf(sv) - c.steer_rate_pen)), 1.0f, q_p2);
+                            if (t >= 2) q_sa = fmaf(sq(sv - sv_prev), 1.0f, q_sa);
+                            sv_prev = sv;
+                        }
+                        q_v = fmaf(sq(v - vdes), 1.0f, q_v);
+                        q_s = fmaf(st, st, q_s);
+                        q_p1 = fmaf(sq(dm::max0_(fabsf(st) - c.steer_max)), 1.0f, q_p1);
+                        q_ydd = fmaf(ydd[i], ydd[i], q_ydd); q_xdd = fmaf(xdd[i], xdd[i], q_xdd);
+                        v_prev = v; st_prev = st;
+                    }
+                }
+                if (live) {
+                    *reinterpret_cast<float4*>(steerg + t0) = make_float4(st8[0], st8[1], st8[2], st8[3]);
+                    if (t0 + 4 < T_) *reinterpret_cast<float4*>(steerg + t0 + 4) = make_float4(st8[4], st8[5], st8[6], st8[7]);
+                }
+                PTC_WAIT();
+                put8(abuf, 0, tid, rvx); put8(abuf, 1, tid, rvy); put8(abuf, 2, tid, rax); put8(abuf, 3, tid, ray); put8(abuf, 4, tid, dlb);
+                PTC_PUBLISH();
+                if (tid == 0) {
+                    fence_after();
+                    const bool first = t0 == 0;
+                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
+                    issue_reduce(tmem, sb, ab, 1, 1, t0, 2, first);     // Uy  = Pd^T r_vy
+                    issue_reduce(tmem, sb, ab, 2, 2, t0, 0, false);     // Ux += Pdd^T r_ax
+                    issue_reduce(tmem, sb, ab, 3, 2, t0, 2, false);     // Uy += Pdd^T r_ay
+                    issue_reduce(tmem, sb, ab, 4, 0, t0, 2, false);     // Uy += P^T (r_lane_ub - r_lane_lb)
+                    commit(bar_m);
+                }
+                pending = true;
+            }
+        }
+        if (live) accg[T_ - 1] = (v_prev - v_prev) / c.dt;
+    }
+    PTC_WAIT();
+    fence_after();
+    {
+        float ux[8], ux2[8], uy[8], uy2[8];
+        tld8(tl + COL_UW + 0, ux); tld8(tl + COL_UW + 8, ux2); tld8(tl + COL_UW + 32, uy); tld8(tl + COL_UW + 40, uy2);
+        tld_wait();
+        if (live) {
+            float* lxg = a.lam_x + (size_t)g * NV; float* lyg = a.lam_y + (size_t)g * NV;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                lxg[j] = lxg[j] - (j < 8 ? ux[j] : ux2[j - 8]);
+                lyg[j] = lyg[j] - (j < 8 ? uy[j] : uy2[j - 8]);
+            }
+            const float res_norm = (sqrtf(q_acc) + sqrtf(q_vel)) + sqrtf(q_lane);
+            const float base = ((((res_norm + 0.1f * sqrtf(q_v)) + 0.1f * ((sqrtf(q_s) + sqrtf(q_sv)) + sqrtf(q_sa))) + 0.1f * (sqrtf(q_p1) + sqrtf(q_p2))) +
+                                0.02f * sqrtf(q_ydd)) + 0.02f * sqrtf(q_xdd);
+            a.res_norm[g] = res_norm; a.cost_base[g] = base;
+        }
+    }
+#undef PTC_WAIT
+#undef PTC_PUBLISH
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}

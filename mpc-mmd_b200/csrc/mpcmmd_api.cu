@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../include/mpcmmd.h"
 #include "k_project.cuh"
+#include "k_project_tc.cuh"
 #include "k_risk.cuh"
 #include "k_inner_cem.cuh"
 #include "k_inner_cem_warp.cuh"
@@ -39,6 +40,7 @@ struct mpcmmd_handle_s {
     int sm_count = 148;
     int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic (MPCMMD_INNER_CEM=auto|warp|cta|generic)
     int E = 0;
+    bool proj_tc = false;      // MPCMMD_PROJ=tc: tensor-core projection kernel (k_project_tc)
     std::vector<void*> allocs;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
     std::map<std::pair<int, int>, int> graph_launches;
@@ -179,6 +181,29 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         if ((int)blk.size() != PROJ_CONST_FLOATS || upload(h, &base, blk.data(), blk.size())) { mpcmmd_destroy(h); return -1; }
         d.proj_const = base; d.P = base; d.Pd = base + 1100; d.Pdd = base + 2200; d.Gx = base + 3300; d.Gy = d.Gx + 77; d.Kx = d.Gy + 88; d.Ky = d.Kx + 154;
     }
+    {   // operands of k_project_tc: each Bernstein matrix as a [4 chunks][112 knots][4 coefficients] image, split x = hi + lo into two
+        // tf32 values (round to nearest, ties away: cvt.rna.tf32.f32), followed by Gx | Gy | Kx | Ky
+        auto rna = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+        std::vector<float> img(ptc::CONST_BYTES / 4, 0.0f);
+        const float* mats[3] = {cfg->P, cfg->Pdot, cfg->Pddot};
+        for (int m = 0; m < 3; m++)
+            for (int t = 0; t < T_; t++)
+                for (int j = 0; j < NV; j++) {
+                    const float x = mats[m][t * NV + j], hi = rna(x), lo = rna(x - hi);
+                    const size_t off = (size_t)(j / 4) * (ptc::KSTR / 4) + (size_t)t * 4 + (j % 4);
+                    img[(size_t)(2 * m) * (ptc::IMG / 4) + off] = hi;
+                    img[(size_t)(2 * m + 1) * (ptc::IMG / 4) + off] = lo;
+                    const size_t offr = (size_t)(t / 4) * (ptc::RSTR / 4) + (size_t)j * 4 + (t % 4);      // transposed: [4-knot chunk][coefficient][knot]
+                    img[ptc::OFF_R / 4 + (size_t)(2 * m) * (ptc::RIMG / 4) + offr] = hi;
+                    img[ptc::OFF_R / 4 + (size_t)(2 * m + 1) * (ptc::RIMG / 4) + offr] = lo;
+                }
+        size_t o = ptc::B_BYTES / 4;
+        const float* sm[4] = {cfg->Gx, cfg->Gy, cfg->Kx, cfg->Ky}; const int cnt[4] = {77, 88, 154, 165};
+        for (int i = 0; i < 4; i++) { memcpy(&img[o], sm[i], cnt[i] * sizeof(float)); o += cnt[i]; }
+        if (upload(h, &d.proj_tc_const, img.data(), img.size())) { mpcmmd_destroy(h); return -1; }
+        const char* pv = getenv("MPCMMD_PROJ");               // "tc": tensor-core projection (tolerance parity, see k_project_tc.cuh)
+        h->proj_tc = pv && !strcmp(pv, "tc");
+    }
     DWork& w = h->w;
     const size_t EB = (size_t)E * B, n = (size_t)nr * np, ncem = (size_t)(B - d.n_el) * NPAR;
 #define AL(p, cnt) if (dalloc(h, &w.p, (cnt))) { mpcmmd_destroy(h); return -1; }
@@ -237,6 +262,8 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     }
     // opt-in shared memory sizes
     if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
+    if (cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ptc::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_project_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project_tc smem opt-in failed"); }
     {
         size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(d, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
@@ -290,10 +317,14 @@ static ProjArgs proj_args(mpcmmd_handle_s* h, int n_ep) {
     ProjArgs p;
     p.n_samples = n_ep * h->d.B; p.B = h->d.B; p.params = h->w.params; p.beq_x = h->beq_x; p.beq_y = h->beq_y; p.v_des = h->w.v_des;
     p.lam_x = h->w.lam_x; p.lam_y = h->w.lam_y; p.s_lane = h->w.s_lane; p.cx = h->w.cx; p.cy = h->w.cy; p.res_norm = h->w.res_norm;
-    p.cost_base = h->w.cost_base; p.acc = h->w.acc; p.steer = h->w.steer;
+    p.cost_base = h->w.cost_base; p.acc = h->w.acc; p.steer = h->w.steer; p.dbg = 0;
     return p;
 }
 static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s) {
+    if (h->proj_tc) {
+        k_project_tc<<<(p.n_samples + ptc::THREADS - 1) / ptc::THREADS, ptc::THREADS, ptc::SMEM_BYTES, s>>>(h->d, p);
+        return 0;
+    }
     const int blocks = (p.n_samples + PROJ_WARPS - 1) / PROJ_WARPS;
     k_project<<<blocks, PROJ_WARPS * 32, PROJ_SMEM_BYTES, s>>>(h->d, p);
     return 0;
@@ -531,6 +562,7 @@ extern "C" int mpcmmd_stage_project(mpcmmd_handle h, int n, const float* params,
     ProjArgs p;
     p.n_samples = n; p.B = n; p.params = params; p.beq_x = beq_x; p.beq_y = beq_y; p.v_des = vd; p.lam_x = lam_x; p.lam_y = lam_y; p.s_lane = s_lane;
     p.cx = cx; p.cy = cy; p.res_norm = res_norm; p.cost_base = cost_base; p.acc = acc; p.steer = steer;
+    { const char* dv = getenv("MPCMMD_PROJ_DEBUG"); p.dbg = dv ? atoi(dv) : 0; }
     launch_project(h, p, 0);
     CK(cudaDeviceSynchronize());
     return 0;
