@@ -27,8 +27,8 @@ constexpr uint32_t RSTR = 16 * 16;                         // 256: bytes between
 constexpr uint32_t RIMG = 26 * RSTR;                       // 6656: one [26 chunks][16 coefficients][4 knots] tf32 image (knots padded to 104)
 constexpr uint32_t OFF_R = 6 * IMG;                        // P_hi P_lo Pd_hi Pd_lo Pdd_hi Pdd_lo, then the same six transposed
 constexpr uint32_t B_BYTES = 6 * IMG + 6 * RIMG;
-constexpr int SMALL = 77 + 88 + 154 + 165;                 // Gx Gy Kx Ky
-constexpr uint32_t CONST_BYTES = B_BYTES + SMALL * 4;      // 84880
+constexpr int SMALL = 77 + 88 + 154 + 165 + 36;            // Gx Gy Kx Ky | fp32 rows P[0] Pd[0] Pdd[0] (+3 pad)
+constexpr uint32_t CONST_BYTES = B_BYTES + SMALL * 4;      // 85024
 constexpr uint32_t MAT = 4096;                             // one [2 chunks][128 rows][4] part of an A operand (8 knots)
 constexpr uint32_t ABUF = 10 * MAT;                        // 5 matrices x (hi, lo)
 constexpr uint32_t OFF_A = (CONST_BYTES + 127) / 128 * 128;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                     const bool ok = t < T_;
                     r_x[i] = ok ? gx[i] - bx : 0.0f; b_x[i] = ok ? bx : 0.0f;
                     r_y[i] = ok ? gy[i] - by : 0.0f; b_y[i] = ok ? by : 0.0f;
-                    dl[i] = (t >= 1 && ok) ? (c.b_lane_ub - __ldg(slr + t - 1)) - (c.b_lane_lb - __ldg(slr + NL + t - 1)) : 0.0f;
+                    dl[i] = (t >= 1 && ok) ? (c.b_lane_ub - slr[t - 1]) - (c.b_lane_lb - slr[NL + t - 1]) : 0.0f;
                     if ((a.dbg & 3) == 1 && live0 && ok) { a.acc[(size_t)g * T_ + t] = gx[i]; a.steer[(size_t)g * T_ + t] = gy[i]; }
                 }
                 PTC_WAIT();
@@ -326,6 +326,14 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                 tld8(tl + 0 * 32 + 8 * sc, xd); tld8(tl + 1 * 32 + 8 * sc, yd); tld8(tl + 2 * 32 + 8 * sc, xdd); tld8(tl + 3 * 32 + 8 * sc, ydd);
                 tld8(tl + 4 * 32 + 8 * sc, yy);
                 tld_wait();
+                if (t0 == 0) {
+                    // knot 0 is pinned by the boundary conditions: with the vehicle's lateral velocity and acceleration at rest the exact steering
+                    // there is 0, where the reference's beta noise model Beta(a|steer|, b|steer|) (cem_helper.py:427-436) is singular.  The
+                    // reference (and k_project) get a rounding-level value from the fp32 dot product; evaluate this one knot the same way.
+                    const float* r0 = sKy + 165;
+                    xd[0] = dot11(r0 + NV, cf); yd[0] = dot11(r0 + NV, cf + NV); xdd[0] = dot11(r0 + 2 * NV, cf); ydd[0] = dot11(r0 + 2 * NV, cf + NV);
+                    yy[0] = dot11(r0, cf + NV);
+                }
                 float rvx[8], rvy[8], rax[8], ray[8], dlb[8], st8[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
