@@ -11,8 +11,9 @@
 //     returned zeros for kind::tf32 with SWIZZLE_NONE on B200, measured; both operands are therefore K-major);
 //   * every product is 4 x kind::tf32 MMAs on an error-free round-to-nearest split x = hi + lo of both operands
 //     (lo*lo, lo*hi, hi*lo, hi*hi, smallest first; fp32 accumulation in TMEM), i.e. ~2^-22 relative per product.
-// The element-wise work between the products (atan2 / unwrap / polar clip / lane slacks / controls / cost norms) stays on the
-// CUDA cores with one thread per sample; unwrap and all finite differences are sequential carries in registers.
+// The element-wise work between the products (polar clip / lane slacks / controls / cost norms) stays on the CUDA cores with one
+// thread per sample; finite differences are sequential carries in registers.  The polar step needs no trigonometry here: the
+// reference's atan2 -> unwrap -> cos / sin chain is the unit vector (x, y) / r (see polar_fast), which a tolerance-parity kernel may use.
 // This variant does NOT reproduce the ascending fma chains of the arithmetic contract: it is tested against the oracle at the
 // tolerance north_star states (1e-4), not bit for bit, and is therefore not the default path.
 #pragma once
@@ -20,21 +21,23 @@
 
 namespace ptc {
 constexpr int THREADS = 128;
-constexpr int NROW = 112;                                  // knots padded to 7 x 16
-constexpr uint32_t KSTR = NROW * 16;                       // 1792: bytes between the 16-byte coefficient chunks of an image
-constexpr uint32_t IMG = 4 * KSTR;                         // 7168: one [4 chunks][112 knots][4 coefficients] tf32 image
+constexpr int NROW = 104;                                  // knots padded to 13 x 8
+constexpr uint32_t KSTR = NROW * 16;                       // 1664: bytes between the 16-byte coefficient chunks of an image
+constexpr uint32_t IMG = 4 * KSTR;                         // 6656: one [4 chunks][104 knots][4 coefficients] tf32 image
 constexpr uint32_t RSTR = 16 * 16;                         // 256: bytes between the 4-knot chunks of a transposed image
 constexpr uint32_t RIMG = 26 * RSTR;                       // 6656: one [26 chunks][16 coefficients][4 knots] tf32 image (knots padded to 104)
 constexpr uint32_t OFF_R = 6 * IMG;                        // P_hi P_lo Pd_hi Pd_lo Pdd_hi Pdd_lo, then the same six transposed
 constexpr uint32_t B_BYTES = 6 * IMG + 6 * RIMG;
 constexpr int SMALL = 77 + 88 + 154 + 165 + 36;            // Gx Gy Kx Ky | fp32 rows P[0] Pd[0] Pdd[0] (+3 pad)
-constexpr uint32_t CONST_BYTES = B_BYTES + SMALL * 4;      // 85024
+constexpr uint32_t CONST_BYTES = B_BYTES + SMALL * 4;      // 81952
 constexpr uint32_t MAT = 4096;                             // one [2 chunks][128 rows][4] part of an A operand (8 knots)
-constexpr uint32_t ABUF = 10 * MAT;                        // 5 matrices x (hi, lo)
+constexpr uint32_t ABUF = 8 * MAT;                         // 4 matrices x (hi, lo); also holds the coefficient operand (4 x 8 KB)
 constexpr uint32_t OFF_A = (CONST_BYTES + 127) / 128 * 128;
 constexpr uint32_t SMEM_BYTES = OFF_A + ABUF + 64;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t COL_UW = 160;                           // columns 0..159: five 32-knot blocks; 160..223: four 16-column reductions
+// knot blocks of the expansion products: 32, 32, 32 and a 16-knot block at 88 whose upper half (knots 96..103) is the one consumed
+// (an M = 128 MMA needs N % 16 == 0 and the images end at knot 103)
 static_assert(CONST_BYTES % 16 == 0, "bulk copy size");
 
 __host__ __device__ constexpr uint32_t idesc(int n, int b_mn) {      // kind::tf32, fp32 accumulate, M = 128, A K-major
@@ -127,9 +130,20 @@ __device__ __forceinline__ void issue_reduce(uint32_t tmem, uint32_t sb, uint32_
     mma4(tmem + COL_UW + acc * 16, ab + 2 * m * MAT, ab + (2 * m + 1) * MAT, img, img + RIMG, RSTR, 128, idesc(16, 0), first);
 }
 __device__ __forceinline__ float sq(float x) { return x * x; }
+// polar re-parametrisation + clip of one (x, y) pair without trigonometry: with alpha = atan2(y, x) (plus any multiple of 2 pi from
+// jnp.unwrap) cos(alpha) = x / r and sin(alpha) = y / r, so the reference's  d = clip((x cos + y sin) / (cos^2 + sin^2))  is clip(r) and the
+// target point is (x, y) * clip(r) / r  [projection.py:73-99, 217-243].  atan2(0, 0) = 0 makes the direction (1, 0) at the origin.
+__device__ __forceinline__ void polar_fast(float x, float y, float lo, float hi, float& bx, float& by) {
+    const float r = sqrtf(x * x + y * y);
+    const float d = dm::clip_(r, lo, hi);
+    const bool origin = r == 0.0f;
+    const float k = d / r;
+    bx = origin ? d : k * x;
+    by = origin ? 0.0f : k * y;
+}
 }  // namespace ptc
 
-__global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs a) {
+__global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs a) {
     using namespace ptc;
     extern __shared__ __align__(128) unsigned char smraw[];
     const uint32_t sb = smem_u32(smraw);
@@ -189,9 +203,30 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
 
     // ---- pass 1: guess derivatives -> unwrap -> polar clip -> P^T r, P^T b  [projection.py:73-131, 158-166]
     {
-        float prev_v = 0.0f, cum_v = 0.0f, prev_a = 0.0f, cum_a = 0.0f;
-        for (int kb = 0; kb < NROW; kb += 32) {
-            const int n = kb < 96 ? 32 : 16, nsc = kb < 96 ? 4 : 1;
+        // lane term of the linear cost first: Wy = P^T (LA_ub - LA_lb), four 8-knot chunks per round  [projection.py:127-131]
+        for (int rd = 0; rd < 4; rd++) {
+            const int nch = rd < 3 ? 4 : 1;
+            PTC_WAIT();
+            for (int m = 0; m < nch; m++) {
+                const int t0 = 8 * (4 * rd + m);
+                float dl[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int t = t0 + i;
+                    dl[i] = (t >= 1 && t < T_) ? (c.b_lane_ub - slr[t - 1]) - (c.b_lane_lb - slr[NL + t - 1]) : 0.0f;
+                }
+                put8(abuf, m, tid, dl);
+            }
+            PTC_PUBLISH();
+            if (tid == 0) {
+                fence_after();
+                for (int m = 0; m < nch; m++) issue_reduce(tmem, sb, ab, m, 0, 8 * (4 * rd + m), 3, rd == 0 && m == 0);
+                commit(bar_m);
+            }
+            pending = true;
+        }
+        for (int blk = 0; blk < 4; blk++) {
+            const int kb = blk < 3 ? 32 * blk : 88, n = blk < 3 ? 32 : 16, nsc = blk < 3 ? 4 : 1, c0 = blk < 3 ? 0 : 8;
             PTC_WAIT();
             put_coef(abuf, tid, cf);
             PTC_PUBLISH();
@@ -200,26 +235,22 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
             PTC_WAIT();
             fence_after();
             for (int sc = 0; sc < nsc; sc++) {
-                const int t0 = kb + 8 * sc;
-                float gx[8], gy[8], r_x[8], b_x[8], r_y[8], b_y[8], dl[8];
-                tld8(tl + 0 * 32 + 8 * sc, gx); tld8(tl + 1 * 32 + 8 * sc, gy);
+                const int t0 = kb + c0 + 8 * sc;
+                float gx[8], gy[8], r_x[8], b_x[8], r_y[8], b_y[8];
+                tld8(tl + 0 * 32 + c0 + 8 * sc, gx); tld8(tl + 1 * 32 + c0 + 8 * sc, gy);
                 tld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int t = t0 + i;
-                    const float raw = dm::atan2_(gy[i], gx[i]);
-                    if (t >= 1) cum_v = cum_v + unwrap_corr(raw - prev_v);
-                    prev_v = raw;
                     float bx, by;
-                    polar_clip(t >= 1 ? raw + cum_v : raw, gx[i], gy[i], c.v_min, c.v_max, bx, by);
+                    polar_fast(gx[i], gy[i], c.v_min, c.v_max, bx, by);
                     const bool ok = t < T_;
                     r_x[i] = ok ? gx[i] - bx : 0.0f; b_x[i] = ok ? bx : 0.0f;
                     r_y[i] = ok ? gy[i] - by : 0.0f; b_y[i] = ok ? by : 0.0f;
-                    dl[i] = (t >= 1 && ok) ? (c.b_lane_ub - slr[t - 1]) - (c.b_lane_lb - slr[NL + t - 1]) : 0.0f;
                     if ((a.dbg & 3) == 1 && live0 && ok) { a.acc[(size_t)g * T_ + t] = gx[i]; a.steer[(size_t)g * T_ + t] = gy[i]; }
                 }
                 PTC_WAIT();
-                put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y); put8(abuf, 4, tid, dl);
+                put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y);
                 PTC_PUBLISH();
                 if (tid == 0) {
                     fence_after();
@@ -227,21 +258,17 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                     issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
                     issue_reduce(tmem, sb, ab, 1, 1, t0, 1, first);     // Wx  = Pd^T b_vx
                     issue_reduce(tmem, sb, ab, 2, 1, t0, 2, first);     // Uy  = Pd^T r_vy
-                    issue_reduce(tmem, sb, ab, 3, 1, t0, 3, first);     // Wy  = Pd^T b_vy
-                    issue_reduce(tmem, sb, ab, 4, 0, t0, 3, false);     // Wy += P^T (LA_ub - LA_lb)
+                    issue_reduce(tmem, sb, ab, 3, 1, t0, 3, false);     // Wy += Pd^T b_vy
                     commit(bar_m);
                 }
                 pending = true;
-                tld8(tl + 2 * 32 + 8 * sc, gx); tld8(tl + 3 * 32 + 8 * sc, gy);
+                tld8(tl + 2 * 32 + c0 + 8 * sc, gx); tld8(tl + 3 * 32 + c0 + 8 * sc, gy);
                 tld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int t = t0 + i;
-                    const float raw = dm::atan2_(gy[i], gx[i]);
-                    if (t >= 1) cum_a = cum_a + unwrap_corr(raw - prev_a);
-                    prev_a = raw;
                     float bx, by;
-                    polar_clip(t >= 1 ? raw + cum_a : raw, gx[i], gy[i], 0.0f, c.a_max, bx, by);
+                    polar_fast(gx[i], gy[i], 0.0f, c.a_max, bx, by);
                     const bool ok = t < T_;
                     r_x[i] = ok ? gx[i] - bx : 0.0f; b_x[i] = ok ? bx : 0.0f;
                     r_y[i] = ok ? gy[i] - by : 0.0f; b_y[i] = ok ? by : 0.0f;
@@ -311,8 +338,8 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
         float v_prev = 0.0f, st_prev = 0.0f, sv_prev = 0.0f;
         float* slw = a.s_lane + (size_t)g * 2 * NL;
         float* accg = a.acc + (size_t)g * T_; float* steerg = a.steer + (size_t)g * T_;
-        for (int kb = 0; kb < NROW; kb += 32) {
-            const int n = kb < 96 ? 32 : 16, nsc = kb < 96 ? 4 : 1;
+        for (int blk = 0; blk < 4; blk++) {
+            const int kb = blk < 3 ? 32 * blk : 88, n = blk < 3 ? 32 : 16, nsc = blk < 3 ? 4 : 1, c0 = blk < 3 ? 0 : 8;
             PTC_WAIT();
             put_coef(abuf, tid, cf);
             PTC_PUBLISH();
@@ -321,10 +348,10 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
             PTC_WAIT();
             fence_after();
             for (int sc = 0; sc < nsc; sc++) {
-                const int t0 = kb + 8 * sc;
+                const int t0 = kb + c0 + 8 * sc;
                 float xd[8], yd[8], xdd[8], ydd[8], yy[8];
-                tld8(tl + 0 * 32 + 8 * sc, xd); tld8(tl + 1 * 32 + 8 * sc, yd); tld8(tl + 2 * 32 + 8 * sc, xdd); tld8(tl + 3 * 32 + 8 * sc, ydd);
-                tld8(tl + 4 * 32 + 8 * sc, yy);
+                tld8(tl + 0 * 32 + c0 + 8 * sc, xd); tld8(tl + 1 * 32 + c0 + 8 * sc, yd); tld8(tl + 2 * 32 + c0 + 8 * sc, xdd);
+                tld8(tl + 3 * 32 + c0 + 8 * sc, ydd); tld8(tl + 4 * 32 + c0 + 8 * sc, yy);
                 tld_wait();
                 if (t0 == 0) {
                     // knot 0 is pinned by the boundary conditions: with the vehicle's lateral velocity and acceleration at rest the exact steering
@@ -339,14 +366,11 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                 for (int i = 0; i < 8; i++) {
                     const int t = t0 + i;
                     const bool ok = t < T_;
-                    // residuals of the re-projected point  [projection.py:217-255]
-                    float bvx, bvy, bax, bay;
-                    polar_clip(dm::atan2_(yd[i], xd[i]), xd[i], yd[i], c.v_min, c.v_max, bvx, bvy);
-                    polar_clip(dm::atan2_(ydd[i], xdd[i]), xdd[i], ydd[i], 0.0f, c.a_max, bax, bay);
+                    // velocity residuals of the re-projected point  [projection.py:217-255]
+                    float bvx, bvy;
+                    polar_fast(xd[i], yd[i], c.v_min, c.v_max, bvx, bvy);
                     rvx[i] = ok ? xd[i] - bvx : 0.0f; rvy[i] = ok ? yd[i] - bvy : 0.0f;
-                    rax[i] = ok ? xdd[i] - bax : 0.0f; ray[i] = ok ? ydd[i] - bay : 0.0f;
                     q_vel = fmaf(rvx[i], rvx[i], q_vel); q_vel = fmaf(rvy[i], rvy[i], q_vel);
-                    q_acc = fmaf(rax[i], rax[i], q_acc); q_acc = fmaf(ray[i], ray[i], q_acc);
                     // lane slacks and residuals at knot t (row t-1 of A_lane_bound)  [projection.py:182-183]
                     float d = 0.0f;
                     if (t >= 1 && ok) {
@@ -358,6 +382,28 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                         d = r1 - r2;
                     }
                     dlb[i] = d;
+                }
+                PTC_WAIT();
+                put8(abuf, 0, tid, rvx); put8(abuf, 1, tid, rvy); put8(abuf, 2, tid, dlb);
+                PTC_PUBLISH();
+                if (tid == 0) {
+                    fence_after();
+                    const bool first = t0 == 0;
+                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
+                    issue_reduce(tmem, sb, ab, 1, 1, t0, 2, first);     // Uy  = Pd^T r_vy
+                    issue_reduce(tmem, sb, ab, 2, 0, t0, 2, false);     // Uy += P^T (r_lane_ub - r_lane_lb)
+                    commit(bar_m);
+                }
+                pending = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int t = t0 + i;
+                    const bool ok = t < T_;
+                    // acceleration residuals
+                    float bax, bay;
+                    polar_fast(xdd[i], ydd[i], 0.0f, c.a_max, bax, bay);
+                    rax[i] = ok ? xdd[i] - bax : 0.0f; ray[i] = ok ? ydd[i] - bay : 0.0f;
+                    q_acc = fmaf(rax[i], rax[i], q_acc); q_acc = fmaf(ray[i], ray[i], q_acc);
                     // controls and cost terms  [cem_helper.py:540-551, :232-262]
                     const float s2v = xd[i] * xd[i] + yd[i] * yd[i];
                     const float v = sqrtf(s2v);
@@ -385,16 +431,12 @@ __global__ void __launch_bounds__(ptc::THREADS, 1) k_project_tc(DCfg c, ProjArgs
                     if (t0 + 4 < T_) *reinterpret_cast<float4*>(steerg + t0 + 4) = make_float4(st8[4], st8[5], st8[6], st8[7]);
                 }
                 PTC_WAIT();
-                put8(abuf, 0, tid, rvx); put8(abuf, 1, tid, rvy); put8(abuf, 2, tid, rax); put8(abuf, 3, tid, ray); put8(abuf, 4, tid, dlb);
+                put8(abuf, 0, tid, rax); put8(abuf, 1, tid, ray);
                 PTC_PUBLISH();
                 if (tid == 0) {
                     fence_after();
-                    const bool first = t0 == 0;
-                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
-                    issue_reduce(tmem, sb, ab, 1, 1, t0, 2, first);     // Uy  = Pd^T r_vy
-                    issue_reduce(tmem, sb, ab, 2, 2, t0, 0, false);     // Ux += Pdd^T r_ax
-                    issue_reduce(tmem, sb, ab, 3, 2, t0, 2, false);     // Uy += Pdd^T r_ay
-                    issue_reduce(tmem, sb, ab, 4, 0, t0, 2, false);     // Uy += P^T (r_lane_ub - r_lane_lb)
+                    issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
+                    issue_reduce(tmem, sb, ab, 1, 2, t0, 2, false);     // Uy += Pdd^T r_ay
                     commit(bar_m);
                 }
                 pending = true;
