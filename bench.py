@@ -169,7 +169,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--projection", default="exact", choices=["exact", "tc"],
+                    help="exact = k_project (bit-exact FP32, the default product path); tc = k_project_tc (tcgen05 kind::tf32 products, 1e-4 stage parity)")
     args = ap.parse_args()
+    if args.projection == "tc":
+        os.environ["MPCMMD_PROJ"] = "tc"          # read by mpcmmd_create
+    else:
+        os.environ.pop("MPCMMD_PROJ", None)
     select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args, emit)
@@ -344,7 +350,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAME, "episodes_per_gpu": E, "costs": list(COSTS), "num_batch": prob.num_batch,
-                           "maxiter_cem": prob.maxiter_cem, "l2": "flushed between timed steps (256 MiB fill)", "parallelism": "episodes sharded %d-way" % world,
+                           "maxiter_cem": prob.maxiter_cem, "projection": args.projection, "l2": "flushed between timed steps (256 MiB fill)", "parallelism": "episodes sharded %d-way" % world,
                            "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
                 "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat, "clocks": clk.summary()}

@@ -206,16 +206,25 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
         // lane term of the linear cost first: Wy = P^T (LA_ub - LA_lb), four 8-knot chunks per round  [projection.py:127-131]
         for (int rd = 0; rd < 4; rd++) {
             const int nch = rd < 3 ? 4 : 1;
-            PTC_WAIT();
-            for (int m = 0; m < nch; m++) {
-                const int t0 = 8 * (4 * rd + m);
-                float dl[8];
+            float su[32], sl2[32];                                       // all loads of the round in flight before the first use
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int t = t0 + i;
-                    dl[i] = (t >= 1 && t < T_) ? (c.b_lane_ub - slr[t - 1]) - (c.b_lane_lb - slr[NL + t - 1]) : 0.0f;
+            for (int i = 0; i < 32; i++) {
+                const int t = 32 * rd + i;
+                const bool ok = t >= 1 && t < T_ && i < 8 * nch;
+                su[i] = ok ? slr[t - 1] : 0.0f; sl2[i] = ok ? slr[NL + t - 1] : 0.0f;
+            }
+            PTC_WAIT();
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                if (m < nch) {
+                    float dl[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int t = 32 * rd + 8 * m + i;
+                        dl[i] = (t >= 1 && t < T_) ? (c.b_lane_ub - su[8 * m + i]) - (c.b_lane_lb - sl2[8 * m + i]) : 0.0f;
+                    }
+                    put8(abuf, m, tid, dl);
                 }
-                put8(abuf, m, tid, dl);
             }
             PTC_PUBLISH();
             if (tid == 0) {

@@ -115,6 +115,71 @@ def test_stage_project_bit_exact(mods, variant):
         _eq(got["lam_x"][i], lx, "lam_x"); _eq(got["lam_y"][i], ly, "lam_y"); _eq(got["s_lane"][i], sl, "s_lane")
 
 
+def _norm_err(got, ref):
+    ref = np.asarray(ref, np.float64); got = np.asarray(got, np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.mark.parametrize("variant,hard", [("static", False), ("static", True), ("dynamic", True)])
+def test_stage_project_tensor_core_within_tolerance(mods, monkeypatch, variant, hard):
+    """k_project_tc (MPCMMD_PROJ=tc: tcgen05 kind::tf32 products on an error-free hi/lo split, TMEM accumulators) against the oracle.
+    Not bit exact by construction; the bar is north_star's 1e-4 relative (max error over the array / max magnitude of the array) on
+    trajectories (cx, cy), controls, costs, multipliers and slacks.  res_norm of a feasible sample is pure round-off (~1e-5 in the
+    reference's own float32), hence the absolute floor.  300 samples = two full 128-sample tiles and a ragged one."""
+    cem_impl, O = mods
+    monkeypatch.setenv("MPCMMD_PROJ", "tc")
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), variant=variant)
+    rng = np.random.default_rng(11)
+    n = 300
+    params = np.concatenate([rng.uniform(0.1, 45 if hard else 30, (n, 4)), rng.normal(0, 12 if hard else 6, (n, 4))], 1).astype(f32)
+    beq_x = np.array([0.0, 5.0, 0.3], f32); beq_y = np.array([1.75 if variant == "static" else -1.75, 0.2, -0.1, 0.0], f32)
+    lam_x = rng.normal(0, 0.5, (n, 11)).astype(f32); lam_y = rng.normal(0, 0.5, (n, 11)).astype(f32)
+    s_lane = np.abs(rng.normal(0, 1, (n, 198))).astype(f32)
+    lam_x[:10] = 0; lam_y[:10] = 0; s_lane[:10] = 0
+    got = prob.stage_project(params, beq_x, beq_y, 15.0, lam_x, lam_y, s_lane)
+    ref = {k: [] for k in got}
+    for i in range(n):
+        lx, ly, sl = lam_x[i].copy(), lam_y[i].copy(), s_lane[i].copy()
+        r = ora.project(params[i], beq_x, beq_y, 15.0, lx, ly, sl)
+        for k in ("cx", "cy", "res_norm", "acc", "steer", "cost_base"):
+            ref[k].append(np.asarray(r[k]))
+        ref["lam_x"].append(lx); ref["lam_y"].append(ly); ref["s_lane"].append(sl)
+    for k in ("cx", "cy", "acc", "steer", "cost_base", "lam_x", "lam_y", "s_lane"):
+        assert not np.isnan(got[k]).any(), k
+        assert _norm_err(got[k], ref[k]) <= 1e-4, (k, _norm_err(got[k], ref[k]))
+    rn = np.asarray(ref["res_norm"], np.float64)
+    err = np.abs(got["res_norm"] - rn)
+    assert err.max() <= 1e-4 * np.abs(rn).max() + 5e-5, (float(err.max()), int(err.argmax()), float(rn[err.argmax()]))
+
+
+def test_solve_with_tensor_core_projection(mods, monkeypatch):
+    """Full cvar / mmd_opt solves with MPCMMD_PROJ=tc: finite, boundary coefficients pinned, and the planned speed profile close to the
+    exact path's.  Trajectories are NOT compared tightly: the reference's first elite stage ranks projection residuals that are pure
+    round-off for feasible samples (cem.py:233), so any two float32 implementations keep different rows."""
+    cem_impl, O = mods
+    args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
+    ora = O.OracleCEM(*args, variant="static")
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    E = 4
+    idx, xo, yo = _episodes(O, ora, E, 4)
+    res = {}
+    for tag in ("exact", "tc"):
+        if tag == "tc":
+            monkeypatch.setenv("MPCMMD_PROJ", "tc")
+        else:
+            monkeypatch.delenv("MPCMMD_PROJ", raising=False)
+        prob = cem_impl.CEM(*args, variant="static", max_episodes=E)
+        res[tag] = {c: prob.solve_batch(c, idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
+                    for c in ("cvar", "mmd_opt")}
+    for c in ("cvar", "mmd_opt"):
+        t, x = res["tc"][c], res["exact"][c]
+        for k in ("cx", "cy", "cost_obs", "cost_lane"):
+            assert np.isfinite(t[k]).all(), (c, k)
+        np.testing.assert_allclose(t["cx"][:, :3], x["cx"][:, :3], rtol=1e-5, atol=1e-5)      # x0, v0, a0 boundary conditions
+        np.testing.assert_allclose(t["cy"][:, :3], x["cy"][:, :3], rtol=1e-5, atol=1e-5)
+        assert np.abs(t["cx"][:, -1] - x["cx"][:, -1]).max() <= 0.25 * np.abs(x["cx"][:, -1]).max()    # distance covered over the horizon
+
+
 def test_stage_noise_bit_exact(mods):
     prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0))
     for idx_mpc, it in ((6745, 0), (1, 19), (9999, 7)):
