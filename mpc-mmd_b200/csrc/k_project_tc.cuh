@@ -20,7 +20,8 @@
 #include "k_project.cuh"
 
 namespace ptc {
-constexpr int THREADS = 128;
+constexpr int THREADS = 128;                               // compute threads (one per sample); warp 4 issues the MMAs
+constexpr int CTA_THREADS = 160;
 constexpr int NROW = 104;                                  // knots padded to 13 x 8
 constexpr uint32_t KSTR = NROW * 16;                       // 1664: bytes between the 16-byte coefficient chunks of an image
 constexpr uint32_t IMG = 4 * KSTR;                         // 6656: one [4 chunks][104 knots][4 coefficients] tf32 image
@@ -59,6 +60,9 @@ __device__ __forceinline__ void mma4(uint32_t d, uint32_t a_hi, uint32_t a_lo, u
     mma(d, al, bh, id, 1u);
     mma(d, ah, bl, id, 1u);
     mma(d, ah, bh, id, 1u);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -143,7 +147,7 @@ __device__ __forceinline__ void polar_fast(float x, float y, float lo, float hi,
 }
 }  // namespace ptc
 
-__global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs a) {
+__global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, ProjArgs a) {
     using namespace ptc;
     extern __shared__ __align__(128) unsigned char smraw[];
     const uint32_t sb = smem_u32(smraw);
@@ -152,11 +156,12 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
     unsigned char* abuf = smraw + OFF_A;
     const uint32_t ab = sb + OFF_A;
     unsigned long long* bar_c = reinterpret_cast<unsigned long long*>(smraw + OFF_A + ABUF);
-    unsigned long long* bar_m = bar_c + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_c + 2);
+    unsigned long long* bar_m = bar_c + 1;                                // MMA group retired (tcgen05.commit)
+    unsigned long long* bar_f = bar_c + 2;                                // operands of a step written by all 128 compute threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_c + 3);
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    if (tid == 0) { mbar_init(bar_c, 1); mbar_init(bar_m, 1); }
+    if (tid == 0) { mbar_init(bar_c, 1); mbar_init(bar_m, 1); mbar_init(bar_f, THREADS); }
     __syncthreads();
     if (tid == 0) bulk_g2s(smraw, c.proj_tc_const, CONST_BYTES, bar_c);
     if (warp == 0) {
@@ -171,6 +176,56 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);         // this warp's 32 TMEM lanes
     mbar_wait(bar_c, 0);
 
+    if (warp == 4) {
+        // ---- MMA issuer: one elected lane replays the step sequence of the compute warps; each step waits until all 128 compute
+        // threads have written their operands (bar_f), issues the step's MMAs and commits them to bar_m
+        if (tid == 4 * 32) {
+            uint32_t fpar = 0;
+#define PTC_STEP() do { mbar_wait(bar_f, fpar); fpar ^= 1u; fence_after(); } while (0)
+            for (int rd = 0; rd < 4; rd++) {                                   // lane term of the linear cost
+                const int nch = rd < 3 ? 4 : 1;
+                PTC_STEP();
+                for (int m = 0; m < nch; m++) issue_reduce(tmem, sb, ab, m, 0, 8 * (4 * rd + m), 3, rd == 0 && m == 0);   // Wy = P^T (LA_ub - LA_lb)
+                commit(bar_m);
+            }
+            for (int pass = 0; pass < 2; pass++) {
+                for (int blk = 0; blk < 4; blk++) {
+                    const int kb = blk < 3 ? 32 * blk : 88, n = blk < 3 ? 32 : 16, nsc = blk < 3 ? 4 : 1, c0 = blk < 3 ? 0 : 8;
+                    PTC_STEP();
+                    issue_expand(tmem, sb, ab, kb, n, pass == 0 ? 4 : 5);
+                    commit(bar_m);
+                    for (int sc = 0; sc < nsc; sc++) {
+                        const int t0 = kb + c0 + 8 * sc;
+                        const bool first = t0 == 0;
+                        PTC_STEP();
+                        if (pass == 0) {
+                            issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
+                            issue_reduce(tmem, sb, ab, 1, 1, t0, 1, first);     // Wx  = Pd^T b_vx
+                            issue_reduce(tmem, sb, ab, 2, 1, t0, 2, first);     // Uy  = Pd^T r_vy
+                            issue_reduce(tmem, sb, ab, 3, 1, t0, 3, false);     // Wy += Pd^T b_vy
+                        } else {
+                            issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
+                            issue_reduce(tmem, sb, ab, 1, 1, t0, 2, first);     // Uy  = Pd^T r_vy
+                            issue_reduce(tmem, sb, ab, 2, 0, t0, 2, false);     // Uy += P^T (r_lane_ub - r_lane_lb)
+                        }
+                        commit(bar_m);
+                        PTC_STEP();
+                        if (pass == 0) {
+                            issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
+                            issue_reduce(tmem, sb, ab, 1, 2, t0, 1, false);     // Wx += Pdd^T b_ax
+                            issue_reduce(tmem, sb, ab, 2, 2, t0, 2, false);     // Uy += Pdd^T r_ay
+                            issue_reduce(tmem, sb, ab, 3, 2, t0, 3, false);     // Wy += Pdd^T b_ay
+                        } else {
+                            issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
+                            issue_reduce(tmem, sb, ab, 1, 2, t0, 2, false);     // Uy += Pdd^T r_ay
+                        }
+                        commit(bar_m);
+                    }
+                }
+            }
+#undef PTC_STEP
+        }
+    } else {
     const int g0 = blockIdx.x * THREADS + tid;
     const bool live0 = g0 < a.n_samples;
     const int g = live0 ? g0 : a.n_samples - 1;                         // idle rows shadow the last sample and store nothing
@@ -178,7 +233,7 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
     const float* bqx = a.beq_x + e * 3; const float* bqy = a.beq_y + e * 4;
     uint32_t par = 0; bool pending = false;
 #define PTC_WAIT() do { if (pending) { mbar_wait(bar_m, par); par ^= 1u; pending = false; } } while (0)
-#define PTC_PUBLISH() do { fence_async_smem(); fence_before(); __syncthreads(); } while (0)
+#define PTC_PUBLISH() do { fence_async_smem(); fence_before(); mbar_arrive(bar_f); } while (0)      // operands written: hand the step to the issuer warp
 
     // ---- x_guess (same fma chains as k_project)  [cem_helper.py:169-230]
     float cf[22];
@@ -227,11 +282,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
                 }
             }
             PTC_PUBLISH();
-            if (tid == 0) {
-                fence_after();
-                for (int m = 0; m < nch; m++) issue_reduce(tmem, sb, ab, m, 0, 8 * (4 * rd + m), 3, rd == 0 && m == 0);
-                commit(bar_m);
-            }
             pending = true;
         }
         for (int blk = 0; blk < 4; blk++) {
@@ -239,7 +289,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
             PTC_WAIT();
             put_coef(abuf, tid, cf);
             PTC_PUBLISH();
-            if (tid == 0) { fence_after(); issue_expand(tmem, sb, ab, kb, n, 4); commit(bar_m); }
             pending = true;
             PTC_WAIT();
             fence_after();
@@ -261,15 +310,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
                 PTC_WAIT();
                 put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y);
                 PTC_PUBLISH();
-                if (tid == 0) {
-                    fence_after();
-                    const bool first = t0 == 0;
-                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
-                    issue_reduce(tmem, sb, ab, 1, 1, t0, 1, first);     // Wx  = Pd^T b_vx
-                    issue_reduce(tmem, sb, ab, 2, 1, t0, 2, first);     // Uy  = Pd^T r_vy
-                    issue_reduce(tmem, sb, ab, 3, 1, t0, 3, false);     // Wy += Pd^T b_vy
-                    commit(bar_m);
-                }
                 pending = true;
                 tld8(tl + 2 * 32 + c0 + 8 * sc, gx); tld8(tl + 3 * 32 + c0 + 8 * sc, gy);
                 tld_wait();
@@ -286,14 +326,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
                 PTC_WAIT();
                 put8(abuf, 0, tid, r_x); put8(abuf, 1, tid, b_x); put8(abuf, 2, tid, r_y); put8(abuf, 3, tid, b_y);
                 PTC_PUBLISH();
-                if (tid == 0) {
-                    fence_after();
-                    issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
-                    issue_reduce(tmem, sb, ab, 1, 2, t0, 1, false);     // Wx += Pdd^T b_ax
-                    issue_reduce(tmem, sb, ab, 2, 2, t0, 2, false);     // Uy += Pdd^T r_ay
-                    issue_reduce(tmem, sb, ab, 3, 2, t0, 3, false);     // Wy += Pdd^T b_ay
-                    commit(bar_m);
-                }
                 pending = true;
             }
         }
@@ -352,7 +384,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
             PTC_WAIT();
             put_coef(abuf, tid, cf);
             PTC_PUBLISH();
-            if (tid == 0) { fence_after(); issue_expand(tmem, sb, ab, kb, n, 5); commit(bar_m); }
             pending = true;
             PTC_WAIT();
             fence_after();
@@ -395,14 +426,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
                 PTC_WAIT();
                 put8(abuf, 0, tid, rvx); put8(abuf, 1, tid, rvy); put8(abuf, 2, tid, dlb);
                 PTC_PUBLISH();
-                if (tid == 0) {
-                    fence_after();
-                    const bool first = t0 == 0;
-                    issue_reduce(tmem, sb, ab, 0, 1, t0, 0, first);     // Ux  = Pd^T r_vx
-                    issue_reduce(tmem, sb, ab, 1, 1, t0, 2, first);     // Uy  = Pd^T r_vy
-                    issue_reduce(tmem, sb, ab, 2, 0, t0, 2, false);     // Uy += P^T (r_lane_ub - r_lane_lb)
-                    commit(bar_m);
-                }
                 pending = true;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -442,12 +465,6 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
                 PTC_WAIT();
                 put8(abuf, 0, tid, rax); put8(abuf, 1, tid, ray);
                 PTC_PUBLISH();
-                if (tid == 0) {
-                    fence_after();
-                    issue_reduce(tmem, sb, ab, 0, 2, t0, 0, false);     // Ux += Pdd^T r_ax
-                    issue_reduce(tmem, sb, ab, 1, 2, t0, 2, false);     // Uy += Pdd^T r_ay
-                    commit(bar_m);
-                }
                 pending = true;
             }
         }
@@ -474,6 +491,7 @@ __global__ void __launch_bounds__(ptc::THREADS, 2) k_project_tc(DCfg c, ProjArgs
     }
 #undef PTC_WAIT
 #undef PTC_PUBLISH
+    }   // compute warps
     fence_before();
     __syncthreads();
     if (warp == 0) {

@@ -323,7 +323,7 @@ static ProjArgs proj_args(mpcmmd_handle_s* h, int n_ep) {
 }
 static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s) {
     if (h->proj_tc) {
-        k_project_tc<<<(p.n_samples + ptc::THREADS - 1) / ptc::THREADS, ptc::THREADS, ptc::SMEM_BYTES, s>>>(h->d, p);
+        k_project_tc<<<(p.n_samples + ptc::THREADS - 1) / ptc::THREADS, ptc::CTA_THREADS, ptc::SMEM_BYTES, s>>>(h->d, p);
         return 0;
     }
     const int blocks = (p.n_samples + PROJ_WARPS - 1) / PROJ_WARPS;
