@@ -41,6 +41,7 @@ struct mpcmmd_handle_s {
     int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic (MPCMMD_INNER_CEM=auto|warp|cta|generic)
     int E = 0;
     bool proj_tc = false;      // MPCMMD_PROJ=tc: tensor-core projection kernel (k_project_tc)
+    bool proj_tc_always = false;
     std::vector<void*> allocs;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
     std::map<std::pair<int, int>, int> graph_launches;
@@ -203,7 +204,8 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         for (int m = 0; m < 3; m++) { memcpy(&img[o], mats[m], NV * sizeof(float)); o += NV; }     // fp32 rows of knot 0
         if (upload(h, &d.proj_tc_const, img.data(), img.size())) { mpcmmd_destroy(h); return -1; }
         const char* pv = getenv("MPCMMD_PROJ");               // "tc": tensor-core projection (tolerance parity, see k_project_tc.cuh)
-        h->proj_tc = pv && !strcmp(pv, "tc");
+        h->proj_tc = pv && (!strcmp(pv, "tc") || !strcmp(pv, "tc-always"));
+        h->proj_tc_always = pv && !strcmp(pv, "tc-always");   // tests / probes: every launch, whatever its size
     }
     DWork& w = h->w;
     const size_t EB = (size_t)E * B, n = (size_t)nr * np, ncem = (size_t)(B - d.n_el) * NPAR;
@@ -322,7 +324,9 @@ static ProjArgs proj_args(mpcmmd_handle_s* h, int n_ep) {
     return p;
 }
 static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s) {
-    if (h->proj_tc) {
+    // MPCMMD_PROJ=tc: the tensor-core kernel for throughput-sized launches.  One of its CTAs walks the 100 knots of 128 samples serially
+    // (~115 us alone on an SM, measured), so small launches (latency regime, e.g. one episode = 100 samples: 29 us) keep the warp-per-sample kernel.
+    if (h->proj_tc && (h->proj_tc_always || p.n_samples >= 64 * h->sm_count)) {
         k_project_tc<<<(p.n_samples + ptc::THREADS - 1) / ptc::THREADS, ptc::CTA_THREADS, ptc::SMEM_BYTES, s>>>(h->d, p);
         return 0;
     }

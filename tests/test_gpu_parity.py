@@ -127,7 +127,7 @@ def test_stage_project_tensor_core_within_tolerance(mods, monkeypatch, variant, 
     trajectories (cx, cy), controls, costs, multipliers and slacks.  res_norm of a feasible sample is pure round-off (~1e-5 in the
     reference's own float32), hence the absolute floor.  300 samples = two full 128-sample tiles and a ragged one."""
     cem_impl, O = mods
-    monkeypatch.setenv("MPCMMD_PROJ", "tc")
+    monkeypatch.setenv("MPCMMD_PROJ", "tc-always")
     prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0), variant=variant)
     rng = np.random.default_rng(11)
     n = 300
@@ -165,7 +165,7 @@ def test_solve_with_tensor_core_projection(mods, monkeypatch):
     res = {}
     for tag in ("exact", "tc"):
         if tag == "tc":
-            monkeypatch.setenv("MPCMMD_PROJ", "tc")
+            monkeypatch.setenv("MPCMMD_PROJ", "tc-always")
         else:
             monkeypatch.delenv("MPCMMD_PROJ", raising=False)
         prob = cem_impl.CEM(*args, variant="static", max_episodes=E)

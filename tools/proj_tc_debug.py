@@ -1,6 +1,6 @@
 """Debug dump of k_project_tc's pass-1 products (MPCMMD_PROJ_DEBUG=1|2) against a float64 NumPy emulation."""
 import os, sys
-os.environ["MPCMMD_PROJ"] = "tc"
+os.environ["MPCMMD_PROJ"] = "tc-always"
 dbg = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 os.environ["MPCMMD_PROJ_DEBUG"] = str(dbg)
 sys.path.insert(1, "/root/repo"); sys.path.insert(1, "/root/repo/mpc-mmd_b200")

@@ -8,7 +8,7 @@ from mpcmmd_b200 import cem_impl
 f32 = np.float32
 args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
 out = {}
-for tag, env in (("fp32", ""), ("tc", "tc")):
+for tag, env in (("fp32", ""), ("tc", "tc-always")):
     os.environ["MPCMMD_PROJ"] = env
     prob = cem_impl.CEM(*args, variant="static", max_episodes=2)
     zi = prob.tables()[0].reshape(100, 8)

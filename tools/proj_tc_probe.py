@@ -1,6 +1,6 @@
 """k_project_tc (MPCMMD_PROJ=tc) against the CPU oracle on seeded inputs: per-output error table and timing."""
 import os, sys, time
-os.environ["MPCMMD_PROJ"] = "tc"
+os.environ["MPCMMD_PROJ"] = "tc-always"
 sys.path.insert(1, "/root/repo"); sys.path.insert(1, "/root/repo/mpc-mmd_b200")
 import numpy as np
 import torch
@@ -36,7 +36,7 @@ for k in got:
 print("sample0 cx got", got["cx"][0][:4], "ref", ref["cx"][0][:4])
 
 import torch
-for tag, env in (("tc", "tc"), ("fp32", "")):
+for tag, env in (("tc", "tc-always"), ("fp32", "")):
     os.environ["MPCMMD_PROJ"] = env
     pr = cem_impl.CEM(*args, variant="static", max_episodes=200)
     nn = 20000

@@ -15,7 +15,7 @@ eps = [O.static_episode(4, k) for k in range(E)]
 tr = [ora.compute_obs_trajectories(*sc) for sc, _ in eps]
 idx = [i for _, i in eps]; xo = np.stack([t[0] for t in tr]); yo = np.stack([t[1] for t in tr])
 res = {}
-for tag, env in (("fp32", ""), ("tc", "tc")):
+for tag, env in (("fp32", ""), ("tc", "tc-always")):
     os.environ["MPCMMD_PROJ"] = env
     prob = cem_impl.CEM(*args, variant="static", max_episodes=E, maxiter_cem=IT)
     res[tag] = prob.solve_batch(os.environ.get("PROBE_COST", "cvar"), idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
