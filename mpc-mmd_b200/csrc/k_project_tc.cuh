@@ -261,12 +261,22 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
         // lane term of the linear cost first: Wy = P^T (LA_ub - LA_lb), four 8-knot chunks per round  [projection.py:127-131]
         for (int rd = 0; rd < 4; rd++) {
             const int nch = rd < 3 ? 4 : 1;
-            float su[32], sl2[32];                                       // all loads of the round in flight before the first use
+            // all loads of the round in flight before the first use, as 8-byte accesses (a row of s_lane is 8-byte aligned: 198 floats).
+            // knot t reads s_lane[t - 1] (upper bound rows) and s_lane[98 + t] (lower bound rows); fu / fl hold indices 32 rd - 2 .. and 32 rd + 98 ..
+            float fu[34], fl[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const int t = 32 * rd + i;
-                const bool ok = t >= 1 && t < T_ && i < 8 * nch;
-                su[i] = ok ? slr[t - 1] : 0.0f; sl2[i] = ok ? slr[NL + t - 1] : 0.0f;
+            for (int k = 0; k < 17; k++) {
+                const int idx = 32 * rd - 2 + 2 * k;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (idx >= 0 && idx < 2 * NL && 2 * k < 8 * nch + 2) v = *reinterpret_cast<const float2*>(slr + idx);
+                fu[2 * k] = v.x; fu[2 * k + 1] = v.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int idx = 32 * rd + 98 + 2 * k;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (idx < 2 * NL && 2 * k < 8 * nch) v = *reinterpret_cast<const float2*>(slr + idx);
+                fl[2 * k] = v.x; fl[2 * k + 1] = v.y;
             }
             PTC_WAIT();
 #pragma unroll
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int t = 32 * rd + 8 * m + i;
-                        dl[i] = (t >= 1 && t < T_) ? (c.b_lane_ub - su[8 * m + i]) - (c.b_lane_lb - sl2[8 * m + i]) : 0.0f;
+                        dl[i] = (t >= 1 && t < T_) ? (c.b_lane_ub - fu[8 * m + i + 1]) - (c.b_lane_lb - fl[8 * m + i]) : 0.0f;
                     }
                     put8(abuf, m, tid, dl);
                 }
@@ -376,7 +386,10 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
     float q_v = 0.0f, q_s = 0.0f, q_sv = 0.0f, q_sa = 0.0f, q_p1 = 0.0f, q_p2 = 0.0f, q_ydd = 0.0f, q_xdd = 0.0f;
     {
         const float vdes = a.v_des[e];
-        float v_prev = 0.0f, st_prev = 0.0f, sv_prev = 0.0f;
+        float v_prev = 0.0f, st_prev = 0.0f, sv_prev = 0.0f, s1_carry = 0.0f;
+        float apend[8];                                                      // acc[t0 - 8 .. t0 - 1] being assembled (acc[t - 1] needs the speed at knot t)
+#pragma unroll
+        for (int i = 0; i < 8; i++) apend[i] = 0.0f;
         float* slw = a.s_lane + (size_t)g * 2 * NL;
         float* accg = a.acc + (size_t)g * T_; float* steerg = a.steer + (size_t)g * T_;
         for (int blk = 0; blk < 4; blk++) {
@@ -401,7 +414,9 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
                     xd[0] = dot11(r0 + NV, cf); yd[0] = dot11(r0 + NV, cf + NV); xdd[0] = dot11(r0 + 2 * NV, cf); ydd[0] = dot11(r0 + 2 * NV, cf + NV);
                     yy[0] = dot11(r0, cf + NV);
                 }
-                float rvx[8], rvy[8], rax[8], ray[8], dlb[8], st8[8];
+                float rvx[8], rvy[8], rax[8], ray[8], dlb[8], st8[8], s1v[8], s2v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { s1v[i] = 0.0f; s2v[i] = 0.0f; }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int t = t0 + i;
@@ -417,16 +432,32 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
                         const float Ay = yy[i];
                         const float s1 = dm::max0_(-Ay + c.b_lane_ub), r1 = (Ay - c.b_lane_ub) + s1;
                         const float s2 = dm::max0_(Ay + c.b_lane_lb), r2 = (-Ay - c.b_lane_lb) + s2;
-                        if (live) { slw[t - 1] = s1; slw[NL + t - 1] = s2; }
+                        s1v[i] = s1; s2v[i] = s2;
                         q_lane = fmaf(r1, r1, q_lane); q_lane = fmaf(r2, r2, q_lane);
                         d = r1 - r2;
                     }
                     dlb[i] = d;
                 }
+                if (live) {
+                    // slacks as 8-byte stores: upper-bound rows s_lane[t - 1] in pairs (t0 - 2, t0 - 1), (t0, t0 + 1), .. with the slack of knot
+                    // t0 - 1 carried from the previous chunk; lower-bound rows s_lane[98 + t] in pairs starting at the even index 98 + t0
+                    // (the pair of chunk 0 touches index 98, which the last chunk rewrites with the upper-bound slack of knot 99)
+                    if (t0 >= 8) *reinterpret_cast<float2*>(slw + t0 - 2) = make_float2(s1_carry, s1v[0]);
+                    if (t0 + 2 < T_) *reinterpret_cast<float2*>(slw + t0) = make_float2(s1v[1], s1v[2]);
+                    if (t0 + 4 < T_) { *reinterpret_cast<float2*>(slw + t0 + 2) = make_float2(s1v[3], s1v[4]); *reinterpret_cast<float2*>(slw + t0 + 4) = make_float2(s1v[5], s1v[6]); }
+                    else slw[t0 + 2] = s1v[3];                                                        // knot 99 -> index 98
+                    *reinterpret_cast<float2*>(slw + 98 + t0) = make_float2(s2v[0], s2v[1]);
+                    *reinterpret_cast<float2*>(slw + 100 + t0) = make_float2(s2v[2], s2v[3]);
+                    if (t0 + 4 < T_) { *reinterpret_cast<float2*>(slw + 102 + t0) = make_float2(s2v[4], s2v[5]); *reinterpret_cast<float2*>(slw + 104 + t0) = make_float2(s2v[6], s2v[7]); }
+                }
+                s1_carry = s1v[7];
                 PTC_WAIT();
                 put8(abuf, 0, tid, rvx); put8(abuf, 1, tid, rvy); put8(abuf, 2, tid, dlb);
                 PTC_PUBLISH();
                 pending = true;
+                float anew[7];
+#pragma unroll
+                for (int i = 0; i < 7; i++) anew[i] = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int t = t0 + i;
@@ -444,7 +475,8 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
                     st8[i] = st;
                     if (ok) {
                         if (t >= 1) {
-                            if (live) accg[t - 1] = (v - v_prev) / c.dt;
+                            const float av = (v - v_prev) / c.dt;
+                            if (i == 0) apend[7] = av; else anew[i - 1] = av;
                             const float sv = st - st_prev;
                             q_sv = fmaf(sv, sv, q_sv);
                             q_p2 = fmaf(sq(dm::max0_(fabsf(sv) - c.steer_rate_pen)), 1.0f, q_p2);
@@ -458,6 +490,12 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
                         v_prev = v; st_prev = st;
                     }
                 }
+                if (live && t0 >= 8) {
+                    *reinterpret_cast<float4*>(accg + t0 - 8) = make_float4(apend[0], apend[1], apend[2], apend[3]);
+                    *reinterpret_cast<float4*>(accg + t0 - 4) = make_float4(apend[4], apend[5], apend[6], apend[7]);
+                }
+#pragma unroll
+                for (int i = 0; i < 7; i++) apend[i] = anew[i];
                 if (live) {
                     *reinterpret_cast<float4*>(steerg + t0) = make_float4(st8[0], st8[1], st8[2], st8[3]);
                     if (t0 + 4 < T_) *reinterpret_cast<float4*>(steerg + t0 + 4) = make_float4(st8[4], st8[5], st8[6], st8[7]);
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
                 pending = true;
             }
         }
-        if (live) accg[T_ - 1] = (v_prev - v_prev) / c.dt;
+        if (live) *reinterpret_cast<float4*>(accg + T_ - 4) = make_float4(apend[0], apend[1], apend[2], (v_prev - v_prev) / c.dt);     // acc[96..98], acc[99] = 0
     }
     PTC_WAIT();
     fence_after();
