@@ -152,6 +152,27 @@ def test_stage_project_tensor_core_within_tolerance(mods, monkeypatch, variant, 
     assert err.max() <= 1e-4 * np.abs(rn).max() + 5e-5, (float(err.max()), int(err.argmax()), float(rn[err.argmax()]))
 
 
+@pytest.mark.parametrize("n", [1, 37, 129])
+def test_stage_project_tensor_core_ragged_tiles(mods, monkeypatch, n):
+    """k_project_tc with fewer samples than a 128-sample tile, and one sample past a full tile: idle TMEM lanes shadow the last
+    sample and store nothing; every live row still meets the 1e-4 bar."""
+    cem_impl, O = mods
+    monkeypatch.setenv("MPCMMD_PROJ", "tc-always")
+    prob, ora = _pair(mods, (5, 2, 0.1, 30, "gaussian", 0.0, 0.0))
+    rng = np.random.default_rng(100 + n)
+    params = np.concatenate([rng.uniform(0.1, 35, (n, 4)), rng.normal(0, 8, (n, 4))], 1).astype(f32)
+    beq_x = np.array([0.0, 5.0, 0.0], f32); beq_y = np.array([1.75, 0.0, 0.0, 0.0], f32)
+    lam_x = rng.normal(0, 0.5, (n, 11)).astype(f32); lam_y = rng.normal(0, 0.5, (n, 11)).astype(f32)
+    s_lane = np.abs(rng.normal(0, 1, (n, 198))).astype(f32)
+    got = prob.stage_project(params, beq_x, beq_y, 15.0, lam_x, lam_y, s_lane)
+    for i in range(n):
+        lx, ly, sl = lam_x[i].copy(), lam_y[i].copy(), s_lane[i].copy()
+        r = ora.project(params[i], beq_x, beq_y, 15.0, lx, ly, sl)
+        for k, rv in (("cx", r["cx"]), ("cy", r["cy"]), ("acc", r["acc"]), ("steer", r["steer"]), ("lam_x", lx), ("lam_y", ly), ("s_lane", sl)):
+            assert _norm_err(got[k][i], rv) <= 1e-4, (i, k, _norm_err(got[k][i], rv))
+        assert abs(float(got["cost_base"][i]) - float(r["cost_base"])) <= 1e-4 * abs(float(r["cost_base"])) + 5e-5
+
+
 def test_solve_with_tensor_core_projection(mods, monkeypatch):
     """Full cvar / mmd_opt solves with MPCMMD_PROJ=tc: finite, boundary coefficients pinned, and the planned speed profile close to the
     exact path's.  Trajectories are NOT compared tightly: the reference's first elite stage ranks projection residuals that are pure
