@@ -31,7 +31,12 @@ struct RiskArgs {
 // obstacle indicator at one (rollout point, obstacle point)  [costs.py:50-60]
 __device__ __forceinline__ float fbar(const DCfg& c, float x, float y, float xo, float yo) {
     float wc = x - xo, ws = y - yo;
-    float cost = (-(wc * wc) / c.a2_obs - (ws * ws) / c.b2_obs) + 1.0f;
+    const float A = wc * wc, B = ws * ws;
+    // exact screen: outside the obstacle's ellipse box the indicator is 0 without the two IEEE divisions.  A >= a^2 makes the rounded quotient
+    // -A/a^2 <= -1 (rounding is monotone and -1 is representable), B/b^2 >= 0, so the rounded sum is <= -1 and cost <= 0 -> max0 = 0; the same with
+    // the roles swapped.  NaN operands fail the screen and take the full path, so NaN propagation is unchanged.
+    if (((A >= c.a2_obs) || (B >= c.b2_obs)) && A == A && B == B) return 0.0f;
+    float cost = (-A / c.a2_obs - B / c.b2_obs) + 1.0f;
     return dm::max0_(cost);
 }
 // one step of the Euler bicycle model  [cem_helper.py:380-400]; `ts` = tan(steer).  The tangent does not depend on the state, so wherever the

@@ -289,3 +289,26 @@ def test_scene_generators_match(O, built):
             assert ia == ib and all(np.array_equal(x, y) for x, y in zip(a, b))
     fl = scenes.flops_per_sample("mmd_opt", 5, 30, 2)
     assert abs(20 * 100 * (fl["project"] + fl["risk"]) / 7.07e9 - 1.0) < 0.02          # cfg1 mmd_opt = 7.07 GFLOP per solve
+
+
+def test_far_obstacle_screen_is_exact():
+    """csrc/k_risk.cuh::fbar skips the two IEEE divisions of the obstacle indicator (costs.py:50-60) when wc^2 >= a^2 or ws^2 >= b^2.
+    The claim behind it, checked here in IEEE float32 at and just above the boundary: there the reference expression
+    (-(wc^2)/a^2 - (ws^2)/b^2) + 1 is <= 0, so max(cost, 0) = 0 exactly."""
+    f = np.float32
+    rng = np.random.default_rng(3)
+    n = 400_000
+    for _ in range(8):
+        a2 = f(rng.uniform(0.5, 60.0)); b2 = f(rng.uniform(0.5, 60.0))
+        edge = np.full(16, a2, f)
+        A = np.maximum(np.concatenate([edge, np.nextafter(edge, f(np.inf)), a2 * (f(1) + rng.uniform(0, 1e-6, n).astype(f)),
+                                       a2 * rng.uniform(1, 1e6, n).astype(f)]).astype(f), a2)
+        B = (b2 * rng.uniform(0, 2, A.size) ** 4).astype(f)
+        cost = ((-A) / a2 - B / b2) + f(1.0)
+        assert cost.dtype == np.float32 and not (cost > 0).any()
+        edge = np.full(16, b2, f)
+        B = np.maximum(np.concatenate([edge, np.nextafter(edge, f(np.inf)), b2 * (f(1) + rng.uniform(0, 1e-6, n).astype(f)),
+                                       b2 * rng.uniform(1, 1e6, n).astype(f)]).astype(f), b2)
+        A = (a2 * rng.uniform(0, 2, B.size) ** 4).astype(f)
+        cost = ((-A) / a2 - B / b2) + f(1.0)
+        assert not (cost > 0).any()
