@@ -127,7 +127,7 @@ __global__ void k_init(DCfg c, DWork w, int n_ep) {
 
 #define PROJ_WARPS 8
 #define PROJ_CONST_FLOATS (3 * T_ * NV + 77 + 88 + 154 + 165)      // P,Pd,Pdd,Gx,Gy,Kx,Ky
-#define PROJ_WARP_FLOATS (24 + 32 + 24 + 9 * T_ + 2 * 200)          // cb, rhs, cc, V0..V8, LA, LB
+#define PROJ_WARP_FLOATS (24 + 32 + 24 + 9 * T_ + 200)              // cb, rhs, cc, V0..V8, LA (= LB: the lane right-hand side is dead before the lane residual is written)
 #define PROJ_SMEM_BYTES ((PROJ_CONST_FLOATS + PROJ_WARPS * PROJ_WARP_FLOATS) * 4)
 
 struct ProjArgs {           // one batch of samples; sample g = e * B + b uses per-episode boundary data
@@ -163,7 +163,16 @@ __device__ __forceinline__ void polar_clip(float alpha, float wx, float wy, floa
     bx = d * cs; by = d * s;
 }
 
-__global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a) {
+// two dot11 chains over one basis row (x coefficients c[0..10], y coefficients c[11..21] held in registers): the same ascending fma chain per
+// output as dot11, half the shared-memory loads
+__device__ __forceinline__ void dot11x2(const float* row, const float (&c)[2 * NV], float& ox, float& oy) {
+    float ax = 0.0f, ay = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; k++) { const float p = row[k]; ax = fmaf(p, c[k], ax); ay = fmaf(p, c[NV + k], ay); }
+    ox = ax; oy = ay;
+}
+
+__global__ void __launch_bounds__(PROJ_WARPS * 32, 4) k_project(DCfg c, ProjArgs a) {
     extern __shared__ __align__(128) float sm[];
     float* sP = sm; float* sPd = sP + T_ * NV; float* sPdd = sPd + T_ * NV;
     float* sGx = sPdd + T_ * NV; float* sGy = sGx + 77; float* sKx = sGy + 88; float* sKy = sKx + 154;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a)
     float* cb = ws; float* rhs = cb + 24; float* cc = rhs + 32;
     float* V0 = cc + 24; float* V1 = V0 + T_; float* V2 = V1 + T_; float* V3 = V2 + T_; float* V4 = V3 + T_;
     float* V5 = V4 + T_; float* V6 = V5 + T_; float* V7 = V6 + T_; float* V8 = V7 + T_;
-    float* LA = V8 + T_; float* LB = LA + 200;
+    float* LA = V8 + T_; float* LB = LA;
     const float* par = a.params + (size_t)g * NPAR;
     const float* bqx = a.beq_x + e * 3; const float* bqy = a.beq_y + e * 4;
     const bool isx = lane < NV; const int j = isx ? lane : lane - NV;      // coefficient index for lanes < 22
@@ -201,9 +210,13 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a)
     }
     __syncwarp();
     // ---- guess derivatives + raw angles  [projection.py:285-289, :77, :91]
+    float cr[2 * NV];                                 // the 22 coefficients in registers: every basis-row element is loaded once and feeds the x and the y chain
+#pragma unroll
+    for (int k = 0; k < 2 * NV; k++) cr[k] = cb[k];
     for (int t = lane; t < T_; t += 32) {
-        float xdg = dot11(sPd + t * NV, cb), ydg = dot11(sPd + t * NV, cb + NV);
-        float xddg = dot11(sPdd + t * NV, cb), yddg = dot11(sPdd + t * NV, cb + NV);
+        float xdg, ydg, xddg, yddg;
+        dot11x2(sPd + t * NV, cr, xdg, ydg);
+        dot11x2(sPdd + t * NV, cr, xddg, yddg);
         V0[t] = xdg; V1[t] = ydg; V2[t] = xddg; V3[t] = yddg;
         V4[t] = dm::atan2_(ydg, xdg); V5[t] = dm::atan2_(yddg, xddg);
     }
@@ -243,16 +256,18 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a)
         float* lamg = (isx ? a.lam_x : a.lam_y) + (size_t)g * NV + j;
         lam = *lamg;
         const float* rA = isx ? V4 : V5; const float* rV = isx ? V6 : V7;
-        float a1 = 0.0f, a2 = 0.0f;
-        for (int t = 0; t < T_; t++) { a1 = fmaf(sPdd[t * NV + j], rA[t], a1); a2 = fmaf(sPd[t * NV + j], rV[t], a2); }
-        lam = (lam - a1) - a2;
         const float* bA = isx ? V0 : V1; const float* bV = isx ? V2 : V3;
-        a1 = 0.0f; a2 = 0.0f;
-        for (int t = 0; t < T_; t++) { a1 = fmaf(sPdd[t * NV + j], bA[t], a1); a2 = fmaf(sPd[t * NV + j], bV[t], a2); }
-        float lin = ((-lam - cb[lane]) - a1) - a2;
+        // five independent ascending chains advance together (each keeps its own order): P^T r (2), P^T b (2) and the first 99 terms of the lane chain
+        float a1 = 0.0f, a2 = 0.0f, b1 = 0.0f, b2 = 0.0f, a3 = 0.0f;
+        for (int t = 0; t < T_; t++) {
+            const float pdd = sPdd[t * NV + j], pd = sPd[t * NV + j];
+            a1 = fmaf(pdd, rA[t], a1); a2 = fmaf(pd, rV[t], a2);
+            b1 = fmaf(pdd, bA[t], b1); b2 = fmaf(pd, bV[t], b2);
+            if (!isx && t < NL) a3 = fmaf(sP[(t + 1) * NV + j], LA[t], a3);
+        }
+        lam = (lam - a1) - a2;
+        float lin = ((-lam - cb[lane]) - b1) - b2;
         if (!isx) {
-            float a3 = 0.0f;
-            for (int i = 0; i < NL; i++) a3 = fmaf(sP[(i + 1) * NV + j], LA[i], a3);
             for (int i = 0; i < NL; i++) a3 = fmaf(-sP[(i + 1) * NV + j], LA[NL + i], a3);
             lin = lin - a3;
         }
@@ -275,12 +290,17 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a)
     }
     __syncwarp();
     // ---- trajectories of the projected coefficients  [projection.py:173-180]
+#pragma unroll
+    for (int k = 0; k < 2 * NV; k++) cr[k] = cc[k];
     for (int t = lane; t < T_; t += 32) {
-        V0[t] = dot11(sPd + t * NV, cc);          // xdot
-        V2[t] = dot11(sPdd + t * NV, cc);         // xddot
-        V8[t] = dot11(sP + t * NV, cc + NV);      // y
-        V1[t] = dot11(sPd + t * NV, cc + NV);     // ydot
-        V3[t] = dot11(sPdd + t * NV, cc + NV);    // yddot
+        float xd, yd, xdd, ydd;
+        dot11x2(sPd + t * NV, cr, xd, yd);
+        dot11x2(sPdd + t * NV, cr, xdd, ydd);
+        V0[t] = xd; V1[t] = yd; V2[t] = xdd; V3[t] = ydd;
+        float acc = 0.0f;                         // y
+#pragma unroll
+        for (int k = 0; k < NV; k++) acc = fmaf(sP[t * NV + k], cr[NV + k], acc);
+        V8[t] = acc;
     }
     __syncwarp();
     // ---- lane slack and residual  [projection.py:182-183]
@@ -320,12 +340,13 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DCfg c, ProjArgs a)
     // ---- multiplier update  [projection.py:267-272]
     if (lane < 2 * NV) {
         const float* rA = isx ? V4 : V5; const float* rV = isx ? V6 : V7;
-        float a1 = 0.0f, a2 = 0.0f;
-        for (int t = 0; t < T_; t++) { a1 = fmaf(sPdd[t * NV + j], rA[t], a1); a2 = fmaf(sPd[t * NV + j], rV[t], a2); }
+        float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        for (int t = 0; t < T_; t++) {
+            a1 = fmaf(sPdd[t * NV + j], rA[t], a1); a2 = fmaf(sPd[t * NV + j], rV[t], a2);
+            if (!isx && t < NL) a3 = fmaf(sP[(t + 1) * NV + j], LB[t], a3);
+        }
         lam = (lam - a1) - a2;
         if (!isx) {
-            float a3 = 0.0f;
-            for (int i = 0; i < NL; i++) a3 = fmaf(sP[(i + 1) * NV + j], LB[i], a3);
             for (int i = 0; i < NL; i++) a3 = fmaf(-sP[(i + 1) * NV + j], LB[NL + i], a3);
             lam = lam - a3;
         }
