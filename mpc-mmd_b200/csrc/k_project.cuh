@@ -174,6 +174,7 @@ __device__ __forceinline__ void dot11x2(const float* row, const float (&c)[2 * N
 
 __global__ void __launch_bounds__(PROJ_WARPS * 32, 4) k_project(DCfg c, ProjArgs a) {
     extern __shared__ __align__(128) float sm[];
+    static_assert(PROJ_CONST_FLOATS % 4 == 0 && PROJ_WARP_FLOATS % 4 == 0, "the per-warp vectors are read with 16-byte loads");
     float* sP = sm; float* sPd = sP + T_ * NV; float* sPdd = sPd + T_ * NV;
     float* sGx = sPdd + T_ * NV; float* sGy = sGx + 77; float* sKx = sGy + 88; float* sKy = sKx + 154;
     // the 15 KB of constant matrices arrive as ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of ~15 loads and stores per thread
@@ -259,11 +260,19 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32, 4) k_project(DCfg c, ProjArgs
         const float* bA = isx ? V0 : V1; const float* bV = isx ? V2 : V3;
         // five independent ascending chains advance together (each keeps its own order): P^T r (2), P^T b (2) and the first 99 terms of the lane chain
         float a1 = 0.0f, a2 = 0.0f, b1 = 0.0f, b2 = 0.0f, a3 = 0.0f;
-        for (int t = 0; t < T_; t++) {
-            const float pdd = sPdd[t * NV + j], pd = sPd[t * NV + j];
-            a1 = fmaf(pdd, rA[t], a1); a2 = fmaf(pd, rV[t], a2);
-            b1 = fmaf(pdd, bA[t], b1); b2 = fmaf(pd, bV[t], b2);
-            if (!isx && t < NL) a3 = fmaf(sP[(t + 1) * NV + j], LA[t], a3);
+        for (int t = 0; t < T_; t += 4) {             // the per-knot vectors are 16-byte aligned: one LDS.128 feeds four steps of a chain
+            const float4 ra = *reinterpret_cast<const float4*>(rA + t), rv = *reinterpret_cast<const float4*>(rV + t);
+            const float4 ba = *reinterpret_cast<const float4*>(bA + t), bv = *reinterpret_cast<const float4*>(bV + t);
+            const float4 la = *reinterpret_cast<const float4*>(LA + t);
+            const float ra_[4] = {ra.x, ra.y, ra.z, ra.w}, rv_[4] = {rv.x, rv.y, rv.z, rv.w}, ba_[4] = {ba.x, ba.y, ba.z, ba.w};
+            const float bv_[4] = {bv.x, bv.y, bv.z, bv.w}, la_[4] = {la.x, la.y, la.z, la.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float pdd = sPdd[(t + q) * NV + j], pd = sPd[(t + q) * NV + j];
+                a1 = fmaf(pdd, ra_[q], a1); a2 = fmaf(pd, rv_[q], a2);
+                b1 = fmaf(pdd, ba_[q], b1); b2 = fmaf(pd, bv_[q], b2);
+                if (!isx && t + q < NL) a3 = fmaf(sP[(t + q + 1) * NV + j], la_[q], a3);
+            }
         }
         lam = (lam - a1) - a2;
         float lin = ((-lam - cb[lane]) - b1) - b2;
@@ -341,9 +350,15 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32, 4) k_project(DCfg c, ProjArgs
     if (lane < 2 * NV) {
         const float* rA = isx ? V4 : V5; const float* rV = isx ? V6 : V7;
         float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        for (int t = 0; t < T_; t++) {
-            a1 = fmaf(sPdd[t * NV + j], rA[t], a1); a2 = fmaf(sPd[t * NV + j], rV[t], a2);
-            if (!isx && t < NL) a3 = fmaf(sP[(t + 1) * NV + j], LB[t], a3);
+        for (int t = 0; t < T_; t += 4) {
+            const float4 ra = *reinterpret_cast<const float4*>(rA + t), rv = *reinterpret_cast<const float4*>(rV + t);
+            const float4 lb = *reinterpret_cast<const float4*>(LB + t);
+            const float ra_[4] = {ra.x, ra.y, ra.z, ra.w}, rv_[4] = {rv.x, rv.y, rv.z, rv.w}, lb_[4] = {lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                a1 = fmaf(sPdd[(t + q) * NV + j], ra_[q], a1); a2 = fmaf(sPd[(t + q) * NV + j], rv_[q], a2);
+                if (!isx && t + q < NL) a3 = fmaf(sP[(t + q + 1) * NV + j], lb_[q], a3);
+            }
         }
         lam = (lam - a1) - a2;
         if (!isx) {
