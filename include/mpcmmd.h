@@ -85,6 +85,8 @@ typedef struct mpcmmd_handle_s *mpcmmd_handle;
 const char *mpcmmd_last_error(void);
 int mpcmmd_version(void);
 
+/* Environment read here: MPCMMD_PROJ = tc | tc-always selects the tensor-core projection kernel (k_project_tc: tcgen05 kind::tf32 products,
+ * 1e-4 stage parity) for throughput-sized / all launches; unset = the bit-exact FP32 kernel.  See INTEGRATION.md. */
 int mpcmmd_create(const mpcmmd_config *cfg, int device, mpcmmd_handle *out);
 int mpcmmd_destroy(mpcmmd_handle h);
 
