@@ -14,6 +14,10 @@
 // The element-wise work between the products (polar clip / lane slacks / controls / cost norms) stays on the CUDA cores with one
 // thread per sample; finite differences are sequential carries in registers.  The polar step needs no trigonometry here: the
 // reference's atan2 -> unwrap -> cos / sin chain is the unit vector (x, y) / r (see polar_fast), which a tolerance-parity kernel may use.
+// Roles: warps 0-3 compute (thread = sample); one lane of warp 4 issues every MMA.  A step = the compute threads write their operand
+// rows, `fence.proxy.async`, arrive on bar_f (128 arrivals); the issuer waits for bar_f, issues the step's MMAs and `tcgen05.commit`s to bar_m;
+// the compute threads wait for bar_m before they overwrite the operand buffer or read the accumulators.  112 KB of shared memory (80 KB of
+// constant images, one `cp.async.bulk`) and 256 TMEM columns per CTA: two CTAs per SM.
 // This variant does NOT reproduce the ascending fma chains of the arithmetic contract: it is tested against the oracle at the
 // tolerance north_star states (1e-4), not bit for bit, and is therefore not the default path.
 #pragma once
@@ -36,7 +40,7 @@ constexpr uint32_t ABUF = 8 * MAT;                         // 4 matrices x (hi, 
 constexpr uint32_t OFF_A = (CONST_BYTES + 127) / 128 * 128;
 constexpr uint32_t SMEM_BYTES = OFF_A + ABUF + 64;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_UW = 160;                           // columns 0..159: five 32-knot blocks; 160..223: four 16-column reductions
+constexpr uint32_t COL_UW = 160;                           // columns 0..159: the five products (xd, yd, xdd, ydd, y) of one 32-knot block; 160..223: the four 16-column reductions Ux, Wx, Uy, Wy
 // knot blocks of the expansion products: 32, 32, 32 and a 16-knot block at 88 whose upper half (knots 96..103) is the one consumed
 // (an M = 128 MMA needs N % 16 == 0 and the images end at knot 103)
 static_assert(CONST_BYTES % 16 == 0, "bulk copy size");
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(ptc::CTA_THREADS, 2) k_project_tc(DCfg c, Proj
     }
     const float* slr = a.s_lane + (size_t)g * 2 * NL;
 
-    // ---- pass 1: guess derivatives -> unwrap -> polar clip -> P^T r, P^T b  [projection.py:73-131, 158-166]
+    // ---- pass 1: guess derivatives -> polar clip (unwrap does not change cos / sin, see polar_fast) -> P^T r, P^T b  [projection.py:73-131, 158-166]
     {
         // lane term of the linear cost first: Wy = P^T (LA_ub - LA_lb), four 8-knot chunks per round  [projection.py:127-131]
         for (int rd = 0; rd < 4; rd++) {
