@@ -5,10 +5,11 @@
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the CPU baseline arm (oracle port, all host threads)
 
 One "step" = the 200-episode static sweep of synthetic_static_obs/main_mpc.py:106-128 solved with BOTH cost
-functions of configs[1] (`cvar` and `mmd_opt`; beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5) = 400 solves per GPU.
-Multi-GPU is weak scaling: every rank solves its own 200 episodes (episode ids rank*200 ...), no data-path
-collective; the only exchange is the final NCCL all_gather of the 26-float per-episode record.
-Prints ONE JSON line on rank 0.
+functions of configs[1] (`cvar` and `mmd_opt`; beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5) = 400 solves.
+Multi-GPU is STRONG scaling, the metric BASELINE.json states ("8 GPU, 200-config sweep"): the 200 episodes are sharded
+over the ranks exactly as mpcmmd_b200/driver.py::shard does (rank r solves k = r, r + W, ...), no data-path collective; the only
+exchange is the NCCL all_gather of the 26-float per-episode record.  `--scaling weak` (200 episodes per GPU) is kept as an option
+and its value is reported under `weak_scaling` in the same line.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -33,19 +34,19 @@ EPISODES = 200
 VARIANT = "static"
 CEM_KW = {}
 WORKLOAD_NAME = ("configs[1]: synthetic_static_obs, cvar + mmd_opt, beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5, "
-                 "200 episodes per GPU (400 solves/step/GPU)")
+                 "200-episode sweep (400 solves/step)")
 METRIC = "MPC solves/sec"
 
 # The default (and the driver's) workload is configs[1].  The other BASELINE configs are parity-test cases (tests/); `--workload` lets
 # them be timed with the same harness for the numbers quoted in DESIGN.md / profiles/ -- those lines are not the headline.
 WORKLOADS = {
-    "cfg2": None,
+    "cfg2": dict(work=dict(WORK), costs=COSTS, episodes=EPISODES, variant=VARIANT, kw={}, name=WORKLOAD_NAME),
     "cfg3": dict(work=dict(num_reduced=5, num_obs=6, noise_level=0.1, num_prime=60, noise="gaussian", acc_const_noise=0.0, steer_const_noise=0.0),
                  costs=("mmd_opt",), episodes=200, variant="dynamic", kw={},
-                 name="configs[2]: synthetic_dynamic_obs, mmd_opt, gaussian noise 0.1, num_obs 6, num_prime 60, num_reduced 5, 200 episodes per GPU"),
+                 name="configs[2]: synthetic_dynamic_obs, mmd_opt, gaussian noise 0.1, num_obs 6, num_prime 60, num_reduced 5, 200-episode sweep"),
     "cfg3b": dict(work=dict(num_reduced=5, num_obs=6, noise_level=0.3, num_prime=60, noise="beta", acc_const_noise=0.0, steer_const_noise=0.0),
                   costs=("mmd_opt",), episodes=200, variant="dynamic", kw={},
-                  name="configs[2]: synthetic_dynamic_obs, mmd_opt, beta noise 0.3, num_obs 6, num_prime 60, num_reduced 5, 200 episodes per GPU"),
+                  name="configs[2]: synthetic_dynamic_obs, mmd_opt, beta noise 0.3, num_obs 6, num_prime 60, num_reduced 5, 200-episode sweep"),
     "cfg5": dict(work=dict(num_reduced=5, num_obs=32, noise_level=0.1, num_prime=100, noise="gaussian", acc_const_noise=0.0, steer_const_noise=0.0),
                  costs=("cvar",), episodes=25, variant="static", kw=dict(num_batch=16384),
                  name="configs[4] (scaled synthetic): cvar, 16384 CEM samples x 32 obstacles x num_prime 100, 25 episodes per GPU per step "
@@ -56,8 +57,6 @@ WORKLOADS = {
 def select_workload(name):
     global WORK, COSTS, EPISODES, VARIANT, CEM_KW, WORKLOAD_NAME
     w = WORKLOADS[name]
-    if w is None:
-        return
     WORK, COSTS, EPISODES, VARIANT, CEM_KW, WORKLOAD_NAME = w["work"], w["costs"], w["episodes"], w["variant"], w["kw"], w["name"]
 
 
@@ -93,14 +92,20 @@ def make_cpu_arm():
     return ora, O, cores
 
 
+def line_config(scaling):
+    """the `config` object of the JSON line: identical in the native and the reference arm (same workload, same parameters)"""
+    return {"workload": WORKLOAD_NAME, "episodes": EPISODES, "costs": list(COSTS), "num_batch": CEM_KW.get("num_batch", 100), "maxiter_cem": 20,
+            "sharding": "episode k -> rank k mod W (strong)" if scaling == "strong" else "%d episodes per rank (weak)" % EPISODES}
+
+
 def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     ora, O, cores = make_cpu_arm()
     REF_EPISODES = [0, 1, 2, 3]          # bounded sample of the sweep per step (about 3.5 s of CPU work per step on 16 threads)
-    sample = "episodes 0-3 of the sweep, %s (%d solves per step), oracle port in the reference's naive formulation, %d host threads" % (
-        " + ".join(COSTS), len(COSTS) * len(REF_EPISODES), cores)
+    sample = "episodes 0-3 of the 200-episode sweep x {%s} = %d solves per step; scalar C port of the reference (oracle, naive formulation), %d host threads" % (
+        ", ".join(COSTS), len(COSTS) * len(REF_EPISODES), cores)
     for _ in range(args.warmup):
         cpu_arm_step(ora, O, REF_EPISODES)
     t0 = time.perf_counter()
@@ -110,9 +115,10 @@ def run_reference(args, emit):
     dt = time.perf_counter() - t0
     val = n / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample_per_step": "%d episodes x %d costs" % (len(REF_EPISODES), len(COSTS))},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": line_config(args.scaling),
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "GPU-over-scalar-C-port figure: the reference's own runtime (XLA:CPU under jax==0.3.23) is absent from this image"},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -151,6 +157,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def shard(total, rank, world, scaling):
+    """strong: the sweep's episodes k = rank, rank + W, ... (driver.py::shard); weak: `total` episodes of its own per rank"""
+    return list(range(rank, total, world)) if scaling == "strong" else list(range(rank * total, rank * total + total))
+
+
+def traffic_per_launch():
+    """dram bytes of one risk-stage launch group of configs[1], from the committed `ncu --set full` capture of this build
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the raw CSV export); None when no capture of this build is committed"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return float(t["dram_bytes_per_risk_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def main():
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout), so everything
     # except the final line is routed to stderr: fd 1 is pointed at fd 2 for the run and the line goes to the saved descriptor.
@@ -167,7 +188,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE's metric): the 200-episode sweep sharded over the ranks; weak: 200 episodes per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE workloads / the weak-scaling value / the batch-1 latency")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--projection", default="exact", choices=["exact", "tc"],
                     help="exact = k_project (bit-exact FP32, the default product path); tc = k_project_tc (tcgen05 kind::tf32 products, 1e-4 stage parity)")
@@ -198,111 +222,120 @@ def main():
     if local != 0:
         G.build()
     from mpcmmd_b200 import CEM, cem_impl, scenes
-    W, K, E = max(args.warmup, 3), args.steps, EPISODES
-
-    prob = CEM(*cem_args(), variant=VARIANT, max_episodes=E, device=local, **CEM_KW)
-    eps = list(range(rank * E, rank * E + E))
-    host = scenes.static_batch(prob, eps, VARIANT)
+    W, K = max(args.warmup, 3), args.steps
     keys = ("idx_mpc", "init_state", "mean_param", "cov_param", "x_obs_traj", "y_obs_traj", "v_des")
-    dev_in = {k: torch.as_tensor(host[k], device=dev) for k in keys}
-    pinned = {k: torch.as_tensor(host[k]).pin_memory() for k in keys}
-    pinned_np = {k: pinned[k].numpy() for k in keys}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    thresholds = {"cvar": 1e-5, "mmd_opt": -prob.ker_wt + 1.0}                    # main_mpc.py:88-97
-    HEAVY = COSTS[-1]                                                             # the cost whose risk stage the roofline describes
-
-    def record(out, cost):
-        """26-float per-episode record [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] gathered over ranks"""
-        rec = torch.cat([torch.as_tensor(eps, device=dev, dtype=torch.float32)[:, None], (out["cost_obs"] <= thresholds[cost]).float()[:, None],
-                         out["cost_obs"][:, None], out["cost_lane"][:, None], out["cx"], out["cy"]], 1)
-        if world > 1:
-            buf = [torch.empty_like(rec) for _ in range(world)]
-            dist.all_gather(buf, rec)
-            rec = torch.cat(buf, 0)
-        return rec
-
-    def step_device():
-        recs = {}
-        for cost in COSTS:
-            out = prob.solve_batch_device(cost, *[dev_in[k] for k in keys])
-            recs[cost] = record(out, cost)
-        return recs
-
-    def step_host():
-        outs = {}
-        for cost in COSTS:
-            outs[cost] = prob.solve_batch(cost, *[pinned_np[k] for k in keys])
-        return outs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`)
-    for _ in range(W):
-        step_device()
-    launches_per_step = 0
-    for cost in COSTS:            # graphs are cached now; count launches per solve batch
-        prob.solve_batch_device(cost, *[dev_in[k] for k in keys]); launches_per_step += prob.last_launch_count()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    class Arm:
+        """one workload on this rank's shard: handle, device-resident and pinned-host inputs, the two step flavours"""
+
+        def __init__(self, scaling):
+            self.eps = shard(EPISODES, rank, world, scaling)
+            self.E = len(self.eps)
+            self.prob = CEM(*cem_args(), variant=VARIANT, max_episodes=max(self.E, 1), device=local, **CEM_KW)
+            self.host = scenes.static_batch(self.prob, self.eps, VARIANT)
+            self.dev_in = {k: torch.as_tensor(self.host[k], device=dev) for k in keys}
+            self.pinned_np = {k: torch.as_tensor(self.host[k]).pin_memory().numpy() for k in keys}
+            self.thresholds = {c: (-self.prob.ker_wt + 1.0 if c in ("mmd_opt", "mmd_random") else 1e-5) for c in COSTS}     # main_mpc.py:88-97
+            self.total_solves = EPISODES * len(COSTS) * (1 if scaling == "strong" else world)
+
+        def record(self, out, cost):
+            """26-float per-episode record [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] gathered over ranks; shards are
+            ragged under strong scaling (200 = 8 x 25 is even, 3- or 7-way is not), so every rank pads to the largest shard"""
+            rec = torch.cat([torch.as_tensor(self.eps, device=dev, dtype=torch.float32)[:, None], (out["cost_obs"] <= self.thresholds[cost]).float()[:, None],
+                             out["cost_obs"][:, None], out["cost_lane"][:, None], out["cx"], out["cy"]], 1)
+            if world > 1:
+                m = (EPISODES + world - 1) // world if len(self.eps) != EPISODES else EPISODES
+                pad = torch.full((m, 26), -1.0, device=dev); pad[:rec.shape[0]] = rec
+                buf = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(buf, pad)
+                rec = torch.cat(buf, 0)
+                rec = rec[rec[:, 0] >= 0]
+            return rec
+
+        def step_device(self):
+            recs = {}
+            for cost in COSTS:
+                out = self.prob.solve_batch_device(cost, *[self.dev_in[k] for k in keys])
+                recs[cost] = self.record(out, cost)
+            return recs
+
+        def step_host(self):
+            return {cost: self.prob.solve_batch(cost, *[self.pinned_np[k] for k in keys]) for cost in COSTS}
+
+        def time_device(self, K, W, clocks=None):
+            """K timed steps, device-resident inputs, CUDA events per step, L2 flushed between steps; returns (ms_total max over ranks, wall, recs, launches/step)"""
+            for _ in range(W):
+                self.step_device()
+            launches = 0
+            for cost in COSTS:            # graphs are cached now; count launches per solve batch
+                self.prob.solve_batch_device(cost, *[self.dev_in[k] for k in keys]); launches += self.prob.last_launch_count()
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                flush.fill_(i & 0xFF)                       # L2 flush between timed steps (outside the event pair)
+                ev[i][0].record()
+                recs = self.step_device()
+                ev[i][1].record()
+            barrier()
+            wall = time.perf_counter() - t0
+            return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)), wall, recs, launches
+
+    # ---- device-resident throughput (`value`) on the headline workload
+    arm = Arm(args.scaling)
+    prob, E = arm.prob, arm.E
+    HEAVY = COSTS[-1]                                                             # the cost whose risk stage the roofline describes
     with ClockSampler(local) as clk:
-        barrier()
-        t_wall0 = time.perf_counter()
-        for i in range(K):
-            flush.fill_(i & 0xFF)                       # L2 flush between timed steps (outside the event pair)
-            ev[i][0].record()
-            recs = step_device()
-            ev[i][1].record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    solves_per_step = E * len(COSTS) * world
-    value = solves_per_step * K / (ms_total * 1e-3)
+        ms_total, t_wall, recs, launches_per_step = arm.time_device(K, W)
+    value = arm.total_solves * K / (ms_total * 1e-3)
     accepted = {c: int(recs[c][:, 1].sum().item()) for c in COSTS}
 
     # ---- end to end through the host-buffer C ABI call (`e2e`): pinned host inputs, H2D + D2H inside the timed region
     for _ in range(2):
-        step_host()
+        arm.step_host()
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        outs = step_host()
+        outs = arm.step_host()
     barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = solves_per_step * K / float(e2e_t.item())
-    h2d = len(COSTS) * sum(int(pinned_np[k].nbytes) for k in keys)
+    e2e_value = arm.total_solves * K / max_over_ranks(time.perf_counter() - t0)
+    h2d = len(COSTS) * sum(int(arm.pinned_np[k].nbytes) for k in keys)
     d2h = len(COSTS) * sum(int(v.nbytes) for v in outs[HEAVY].values())
-    same = all(np.array_equal(outs[c]["cx"], recs[c][rank * E:(rank + 1) * E, 4:15].cpu().numpy()) for c in COSTS)
+    mine = {c: recs[c][torch.isin(recs[c][:, 0], torch.as_tensor(arm.eps, device=dev, dtype=torch.float32))] for c in COSTS}     # this rank's rows of the gathered records
+    same = all(np.array_equal(outs[c]["cx"], mine[c][torch.argsort(mine[c][:, 0])][:, 4:15].cpu().numpy()) for c in COSTS)        # arm.eps ascends
 
-    # ---- roofline of the dominant kernel (k_risk_opt: rollouts + reduced-set CEM + risk), launch-by-launch CUDA events
-    prob.solve_batch_device(HEAVY, *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+    # ---- roofline of the dominant kernel group (risk stage of the heavy cost), launch-by-launch CUDA events on the launching stream
+    prob.solve_batch_device(HEAVY, *[arm.dev_in[k] for k in keys]); torch.cuda.synchronize()
     prof = prob.profile_solve(HEAVY, E)
     prof_cvar = None
     if "cvar" in COSTS and HEAVY != "cvar":
-        prob.solve_batch_device("cvar", *[dev_in[k] for k in keys]); torch.cuda.synchronize()
+        prob.solve_batch_device("cvar", *[arm.dev_in[k] for k in keys]); torch.cuda.synchronize()
         prof_cvar = prob.profile_solve("cvar", E)
     fl = scenes.flops_per_sample(HEAVY, WORK["num_reduced"], WORK["num_prime"], WORK["num_obs"])
     flops_per_launch = fl["risk"] * prob.num_batch * E
     avg_launch_s = prof["ms"]["risk"] * 1e-3 / prof["launches"]["risk"]
     peak_tf, sm_count = cem_impl.fp32_peak(local)
     achieved = flops_per_launch / avg_launch_s / 1e12
-    # dram bytes per risk-stage launch from the committed ncu --set full captures (profiles/r01_v12_summary.md, r01_v9_summary.md):
-    # k_inner_cem_fast 45 + 12 MB, k_rollouts<ROLL_OPT> 19 + 28 MB at the cfg2 shape (k_opt_risk not captured, < 5 MB of controls); null for the
-    # other workloads
-    traffic = 104.0e6 if (args.workload == "cfg2") else None
-    roofline = {"bound": "fp32", "kernel": ("k_rollouts + k_inner_cem_fast<5> + k_opt_risk (mother rollouts, reduced-set inner CEM, MMD risk)" if HEAVY == "mmd_opt"
+    traffic, traffic_src = traffic_per_launch() if (args.workload == "cfg2" and world == 1) else (None, None)
+    roofline = {"bound": "fp32", "kernel": ("risk stage of mmd_opt: k_rollouts<ROLL_OPT> + reduced-set inner CEM (%s) + k_opt_risk" % prob.inner_cem_path() if HEAVY == "mmd_opt"
                                             else "k_rollouts (noisy rollouts + %s risk)" % HEAVY), "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: register-resident FP32 fma micro-kernel (MEASURED_PEAKS.json has no FP32 figure)",
-                "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "sm_count": sm_count,
+                "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "sm_count": sm_count, "episodes_per_launch": E,
+                "xu_peaks_measured": cem_impl.xu_peaks(local),
                 "kernel_share_of_%s_solve" % HEAVY: prof["ms"]["risk"] / prof["ms"]["total"],
                 "%s_ms_by_kernel" % HEAVY: prof["ms"]}
     if prof_cvar:
@@ -310,9 +343,10 @@ def main():
 
     # ---- per-solve latency at batch = 1 (BASELINE.json's second headline)
     lat = {}
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         p1 = CEM(*cem_args(), variant=VARIANT, max_episodes=1, device=local, **CEM_KW)
-        one = {k: dev_in[k][:1].contiguous() for k in keys}
+        one = {k: arm.dev_in[k][:1].contiguous() for k in keys}
+        host = arm.host
         for cost in COSTS:
             for _ in range(5):
                 p1.solve_batch_device(cost, *[one[k] for k in keys])
@@ -335,6 +369,27 @@ def main():
                          "p50_ms_host_api": float(np.percentile(tw, 50)), "p95_ms_host_api": float(np.percentile(tw, 95)),
                          "ms_by_kernel_ungraphed": p1.profile_solve(cost, 1)["ms"]}
         del p1
+    del arm, prob
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE workloads and the weak-scaled value, device-resident, same timing rules (extra keys; not the headline)
+    extras, weak = {}, None
+    if not args.no_extras and args.workload == "cfg2":
+        if args.scaling == "strong" and world > 1:
+            a2 = Arm("weak")
+            ms2, _, _, _ = a2.time_device(2, 3)
+            weak = {"value": a2.total_solves * 2 / (ms2 * 1e-3), "unit": "solves/s", "episodes_per_gpu": EPISODES, "ms_per_step": ms2 / 2}
+            del a2
+            torch.cuda.empty_cache()
+        for name, scal in (("cfg3", args.scaling), ("cfg3b", args.scaling), ("cfg5", "weak")):
+            select_workload(name)
+            a3 = Arm(scal)
+            ms3, _, r3, _ = a3.time_device(2, 3)
+            extras[name] = {"workload": WORKLOAD_NAME, "value": a3.total_solves * 2 / (ms3 * 1e-3), "unit": "solves/s", "ms_per_step": ms3 / 2,
+                            "scaling": scal, "episodes_this_rank": a3.E, "accepted": {c: int(r3[c][:, 1].sum().item()) for c in COSTS}}
+            del a3
+            torch.cuda.empty_cache()
+        select_workload(args.workload)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -344,16 +399,17 @@ def main():
         n = cpu_arm_step(ora, O, list(range(12)))
         dt = time.perf_counter() - t0
         cpu = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": "episodes 0-11 of the sweep x {%s} = %d solves in %.1f s; oracle port (C, reference's naive formulation), %d host threads" % (", ".join(COSTS), n, dt, cores)}
+               "sample": "episodes 0-11 of the sweep x {%s} = %d solves in %.1f s; oracle port (scalar C, reference's naive formulation; NOT XLA:CPU), %d host threads" % (", ".join(COSTS), n, dt, cores)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD_NAME, "episodes_per_gpu": E, "costs": list(COSTS), "num_batch": prob.num_batch,
-                           "maxiter_cem": prob.maxiter_cem, "projection": args.projection, "l2": "flushed between timed steps (256 MiB fill)", "parallelism": "episodes sharded %d-way" % world,
-                           "accepted": accepted, "wall_s_timed_region": t_wall},
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": line_config(args.scaling),
+                "details": {"episodes_this_rank": E, "projection": args.projection, "l2": "flushed between timed steps (256 MiB fill)",
+                            "parallelism": "episodes sharded %d-way, no data-path collective" % world, "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
-                "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat, "clocks": clk.summary()}
+                "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat,
+                "other_workloads": extras, "weak_scaling": weak, "clocks": clk.summary()}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -103,6 +103,8 @@ int mpcmmd_solve_host(mpcmmd_handle h, int cost_kind, int n_ep, const int32_t *i
 
 /* Number of kernel launches the last mpcmmd_solve on this handle issued (graph nodes). */
 int mpcmmd_last_launch_count(mpcmmd_handle h);
+/* Reporting aid: name of the reduced-set inner-CEM kernel path this handle's mmd_opt launches take (static string). */
+const char *mpcmmd_inner_cem_path(mpcmmd_handle h);
 
 /* Measurement aid: re-runs the solve staged by the previous mpcmmd_solve* call launch by launch (no graph) with a
  * CUDA event after every kernel on the launching stream.  ms[5] = device milliseconds of {setup, projection,
@@ -125,6 +127,9 @@ int mpcmmd_validate_host(int device, int n_ep, int n_roll, int num_prime, int nu
 
 /* Measured FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the roofline denominator of the FP32-bound kernels. */
 int mpcmmd_fp32_peak(int device, float *tflops, int *sm_count);
+/* Measured special-function-unit peaks (thread-level operations per second / 1e9): gops[0] = ex2.approx (MUFU.EX2), gops[1] = IEEE
+ * div.rn.f32, gops[2] = IEEE sqrt.rn.f32 -- the denominators for the XU-bound kernels. */
+int mpcmmd_xu_peaks(int device, float *gops);
 
 /* ---- stage entry points (teacher-forced parity tests; all DEVICE pointers, synchronous) ---- */
 

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/mpcmmd.h"
@@ -14,6 +15,8 @@
 #include "k_risk.cuh"
 #include "k_inner_cem.cuh"
 #include "k_inner_cem_warp.cuh"
+#include "k_inner_split.cuh"
+#include "k_inner_pipe.cuh"
 #include "k_select.cuh"
 #include "k_validate.cuh"
 
@@ -22,6 +25,21 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 extern "C" const char* mpcmmd_last_error(void) { return g_err.c_str(); }
+
+// Dynamic shared memory opt-in of a kernel is a per-(device, function) attribute shared by every handle of the process: it is only ever RAISED
+// (a second handle with a smaller configuration must not lower the limit under a live handle whose graphs ask for more).
+static std::mutex g_smem_mu;
+static std::map<std::pair<int, const void*>, size_t> g_smem_max;
+static int raise_smem(int device, const void* fn, size_t bytes, bool carveout_max = false) {
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t& cur = g_smem_max[std::make_pair(device, fn)];
+    if (bytes > cur) {
+        if (bytes > 48 * 1024 || cur > 0) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    if (carveout_max) CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
 extern "C" int mpcmmd_version(void) { return 100; }
 
 struct mpcmmd_handle_s {
@@ -35,10 +53,13 @@ struct mpcmmd_handle_s {
     int* ridx = nullptr;       // [E*B][nr] reduced sets (k_inner_cem_fast -> k_opt_risk)
     float* bscratch = nullptr; // [E*B][S][nr+1] row records of k_inner_cem_fast
     float* ctrl = nullptr;     // [E*B][2][nr*np] noisy controls (k_rollouts -> k_opt_risk)
+    float* throws = nullptr;        // [E*B][nm+1][ICP_TH_LD] candidate-elite rows of the pipelined inner CEM (k_inner_pipe.cuh)
+    int pipe_minb = 8;              // CTAs per SM the pipelined kernel is compiled for (MPCMMD_PIPE_MINB=8|9|12)
+    float* split_state = nullptr;   // [E*B][SplitLayout::total] chain blocks of the phase-split inner CEM (k_inner_split.cuh)
     float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
     int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
     int sm_count = 148;
-    int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic (MPCMMD_INNER_CEM=auto|warp|cta|generic)
+    int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic, 4 CTA-per-chain latency build, 5 phase-split (MPCMMD_INNER_CEM=auto|warp|cta|generic|lat|split)
     int E = 0;
     bool proj_tc = false;      // MPCMMD_PROJ=tc: tensor-core projection kernel (k_project_tc)
     bool proj_tc_always = false;
@@ -87,15 +108,16 @@ static bool inner_cem_is_fast(const DCfg& d) {
 // many that a small batch leaves SMs idle (latency at batch = 1 episode)
 // latency regime of the num_reduced-rollout costs: with one thread per rollout the launch cannot fill the GPU, so the controls are drawn by
 // whole CTAs first (RollArgs::stage_ctrl)
-static int roll_stage_ctrl(const DCfg& d, int kind, int n_samples) {
-    return kind != MPCMMD_COST_MMD_OPT && (long long)n_samples * d.nr < 2LL * 148 * ROLL_THREADS;
+static int roll_stage_ctrl(const mpcmmd_handle_s* h, int kind, int n_samples) {
+    return kind != MPCMMD_COST_MMD_OPT && (long long)n_samples * h->d.nr < 2LL * h->sm_count * ROLL_THREADS;
 }
-static int roll_spb(const DCfg& d, int kind, int n_samples) {
+static int roll_spb(const mpcmmd_handle_s* h, int kind, int n_samples) {
+    const DCfg& d = h->d;
     const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
-    const int stage = roll_stage_ctrl(d, kind, n_samples);
+    const int stage = roll_stage_ctrl(h, kind, n_samples);
     int spb = ROLL_THREADS / R; if (spb < 1) spb = 1; if ((kind == MPCMMD_COST_MMD_OPT || stage) && spb > 8) spb = 8;
     while (spb > 1 && (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage) * sizeof(float) > 96 * 1024) spb--;
-    while (spb > 1 && (n_samples + spb - 1) / spb < 4 * 148) spb--;
+    while (spb > 1 && (n_samples + spb - 1) / spb < 4 * h->sm_count) spb--;
     return spb;
 }
 static size_t roll_smem_for(const DCfg& d, int kind, int spb, int stage) {
@@ -103,14 +125,38 @@ static size_t roll_smem_for(const DCfg& d, int kind, int spb, int stage) {
     return (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage) * sizeof(float);
 }
 // largest dynamic shared memory any launch of this handle can ask for (opt-in at create)
-static size_t roll_smem(const DCfg& d, int kind) {
-    const size_t a = roll_smem_for(d, kind, roll_spb(d, kind, 1 << 30), 0), b = roll_smem_for(d, kind, roll_spb(d, kind, 1), roll_stage_ctrl(d, kind, 1));
+static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
+    const DCfg& d = h->d;
+    const size_t a = roll_smem_for(d, kind, roll_spb(h, kind, 1 << 30), 0), b = roll_smem_for(d, kind, roll_spb(h, kind, 1), roll_stage_ctrl(h, kind, 1));
     size_t c = 0;
     for (int spb = 1; spb <= 8; spb++) { const size_t v = roll_smem_for(d, kind, spb, kind != MPCMMD_COST_MMD_OPT); if (v <= 96 * 1024 && v > c) c = v; }
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4 };
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6 };
+#define INNER_DEFAULT_THROUGHPUT INNER_CTA
+typedef void (*pipe_fn)(DCfg, RollArgs, float*);
+// the pipelined kernel stages the mother features through its row buffer: (S - ne) rows of nm + 1 (odd stride) must hold nm x 22 floats
+static bool pipe_ok(const DCfg& d) { return inner_cem_is_fast(d) && (d.S_in - d.n_el_in) * ((d.nm + 1) | 1) >= d.nm * 2 * NV; }
+static pipe_fn pipe_kernel(int nr, int minb) {
+#define PK(N) (minb >= 12 ? k_inner_cem_pipe<N, 12> : minb == 9 ? k_inner_cem_pipe<N, 9> : k_inner_cem_pipe<N, 8>)
+    switch (nr) { case 2: return PK(2); case 3: return PK(3); case 4: return PK(4); case 5: return PK(5); default: return nullptr; }
+#undef PK
+}
+typedef void (*split_dist_fn)(DCfg, SplitArgs);
+typedef void (*split_it_fn)(DCfg, SplitArgs, int);
+struct SplitKernels { split_dist_fn dist; split_it_fn eval, update; };
+static SplitKernels split_kernels(int nr) {
+    switch (nr) {
+        case 2: return {k_icem_dist<2>, k_icem_eval<2>, k_icem_update<2>};
+        case 3: return {k_icem_dist<3>, k_icem_eval<3>, k_icem_update<3>};
+        case 4: return {k_icem_dist<4>, k_icem_eval<4>, k_icem_update<4>};
+        case 5: return {k_icem_dist<5>, k_icem_eval<5>, k_icem_update<5>};
+        default: return {nullptr, nullptr, nullptr};
+    }
+}
+static size_t split_eval_smem(const DCfg& d) { const int dd = d.nm + 1; return (size_t)(al4(d.nm * d.nm) + (dd + 1) * al4(dd)) * sizeof(float); }
+static size_t split_update_smem(const DCfg& d) { return (size_t)ICU_WARPS * upd_layout(d.nr).total * sizeof(float); }
 static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_WARP) switch (d.nr) {
         case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
@@ -138,6 +184,7 @@ static size_t inner_cem_smem_kind(const DCfg& d, int kind) {
     return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
 }
 
+static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device);
 extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle* out) {
     if (!cfg || !out) return fail("mpcmmd_create: null argument");
     int ndev = 0;
@@ -152,9 +199,19 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     if (cfg->num_obs < 1 || E < 1) return fail("mpcmmd_create: num_obs and max_episodes must be >= 1");
     if (cfg->num_samples_cem > RISKO_THREADS * 8 || cfg->num_ellite_beta < 2 || cfg->num_ellite_beta >= cfg->num_samples_cem)
         return fail("mpcmmd_create: bad inner-CEM sizes");
-    if (cfg->maxiter_beta_cem > 64 || cfg->maxiter_beta_cem > SEL_THREADS) return fail("mpcmmd_create: maxiter_beta_cem too large");
+    if (cfg->maxiter_beta_cem < 1 || cfg->maxiter_beta_cem > 64 || cfg->maxiter_beta_cem > SEL_THREADS) return fail("mpcmmd_create: maxiter_beta_cem must be in [1, 64]");
+    if (cfg->maxiter_cem < 1 || cfg->maxiter_cem > 4096) return fail("mpcmmd_create: maxiter_cem must be in [1, 4096]");
+    if (cfg->ellite_num < 1) return fail("mpcmmd_create: ellite_num must be >= 1");
+    if (cfg->noise_kind != 0 && cfg->noise_kind != 1) return fail("mpcmmd_create: noise_kind must be 0 (gaussian) or 1 (beta)");
+    if (B < 1 || B > (1 << 20)) return fail("mpcmmd_create: num_batch must be in [1, 2^20]");
     mpcmmd_handle_s* h = new mpcmmd_handle_s();
     h->device = device; h->cfg = *cfg; h->E = E;
+    if (create_body(h, cfg, device)) { mpcmmd_destroy(h); return -1; }      // one cleanup path: every failure after the allocation frees the handle and its device memory
+    *out = h;
+    return 0;
+}
+static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device) {
+    const int B = cfg->num_batch, np = cfg->num_prime, nr = cfg->num_reduced, nm = nr * nr, E = cfg->max_episodes;
     DCfg& d = h->d;
     d.B = B; d.np = np; d.nr = nr; d.nm = nm; d.O = cfg->num_obs; d.iters = cfg->maxiter_cem; d.n_el = cfg->ellite_num;
     d.n_el_cost = cfg->ellite_num_cost; d.noise_kind = cfg->noise_kind; d.S_in = cfg->num_samples_cem; d.iters_in = cfg->maxiter_beta_cem;
@@ -170,16 +227,16 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     d.one_m_alpha_cov = cfg->one_minus_alpha_cov; d.alpha_cov = cfg->alpha_cov;
     d.sigma_clip = cfg->sigma_clip; d.inv_nm = (float)(1.0 / nm); d.m2_inv_nm = (float)(-2.0 * (1.0 / nm)); d.beta_del = (float)(1.0 / nr);
     d.sigma_random = cfg->sigma_random;
-#define UP(dst, src, n) if (upload(h, &d.dst, cfg->src, (n))) { mpcmmd_destroy(h); return -1; }
+#define UP(dst, src, n) if (upload(h, &d.dst, cfg->src, (n))) return -1;
     UP(Wfit, Wfit, (size_t)NV * np)
 #undef UP
     {   // P | Pd | Pdd | Gx | Gy | Kx | Ky in one block (cudaMalloc: 256-byte aligned), the layout k_project's shared memory mirrors
         const float* src[7] = {cfg->P, cfg->Pdot, cfg->Pddot, cfg->Gx, cfg->Gy, cfg->Kx, cfg->Ky};
         const int cnt[7] = {1100, 1100, 1100, 77, 88, 154, 165};
         std::vector<float> blk; blk.reserve(PROJ_CONST_FLOATS);
-        for (int i = 0; i < 7; i++) { if (!src[i]) { mpcmmd_destroy(h); return fail("mpcmmd_create: null matrix pointer in config"); } blk.insert(blk.end(), src[i], src[i] + cnt[i]); }
+        for (int i = 0; i < 7; i++) { if (!src[i]) return fail("mpcmmd_create: null matrix pointer in config"); blk.insert(blk.end(), src[i], src[i] + cnt[i]); }
         const float* base = nullptr;
-        if ((int)blk.size() != PROJ_CONST_FLOATS || upload(h, &base, blk.data(), blk.size())) { mpcmmd_destroy(h); return -1; }
+        if ((int)blk.size() != PROJ_CONST_FLOATS || upload(h, &base, blk.data(), blk.size())) return -1;
         d.proj_const = base; d.P = base; d.Pd = base + 1100; d.Pdd = base + 2200; d.Gx = base + 3300; d.Gy = d.Gx + 77; d.Kx = d.Gy + 88; d.Ky = d.Kx + 154;
     }
     {   // operands of k_project_tc: each Bernstein matrix as a [4 chunks][112 knots][4 coefficients] image, split x = hi + lo into two
@@ -202,14 +259,14 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
         const float* sm[4] = {cfg->Gx, cfg->Gy, cfg->Kx, cfg->Ky}; const int cnt[4] = {77, 88, 154, 165};
         for (int i = 0; i < 4; i++) { memcpy(&img[o], sm[i], cnt[i] * sizeof(float)); o += cnt[i]; }
         for (int m = 0; m < 3; m++) { memcpy(&img[o], mats[m], NV * sizeof(float)); o += NV; }     // fp32 rows of knot 0
-        if (upload(h, &d.proj_tc_const, img.data(), img.size())) { mpcmmd_destroy(h); return -1; }
+        if (upload(h, &d.proj_tc_const, img.data(), img.size())) return -1;
         const char* pv = getenv("MPCMMD_PROJ");               // "tc": tensor-core projection (tolerance parity, see k_project_tc.cuh)
         h->proj_tc = pv && (!strcmp(pv, "tc") || !strcmp(pv, "tc-always"));
         h->proj_tc_always = pv && !strcmp(pv, "tc-always");   // tests / probes: every launch, whatever its size
     }
     DWork& w = h->w;
     const size_t EB = (size_t)E * B, n = (size_t)nr * np, ncem = (size_t)(B - d.n_el) * NPAR;
-#define AL(p, cnt) if (dalloc(h, &w.p, (cnt))) { mpcmmd_destroy(h); return -1; }
+#define AL(p, cnt) if (dalloc(h, &w.p, (cnt))) return -1;
     AL(params, EB * NPAR) AL(lam_x, EB * NV) AL(lam_y, EB * NV) AL(s_lane, EB * 2 * NL) AL(mean, (size_t)E * NPAR) AL(cov, (size_t)E * 64)
     AL(cx, EB * NV) AL(cy, EB * NV) AL(res_norm, EB) AL(cost_base, EB) AL(acc, EB * T_) AL(steer, EB * T_) AL(risk, EB) AL(lane, EB)
     AL(beta, EB * nr) AL(sigma, EB) AL(res_beta, EB * d.iters_in)
@@ -221,13 +278,13 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     AL(o_cx, (size_t)E * NV) AL(o_cy, (size_t)E * NV) AL(o_lane, E) AL(o_obs, E) AL(o_beta, (size_t)E * nr) AL(o_sigma, E)
     AL(o_res_beta, (size_t)E * d.iters_in) AL(o_sel, (size_t)E * d.iters)
 #undef AL
-    if (dalloc(h, &h->beq_x, (size_t)E * 3) || dalloc(h, &h->beq_y, (size_t)E * 4) || dalloc(h, &h->state0, (size_t)E * 5)) { mpcmmd_destroy(h); return -1; }
+    if (dalloc(h, &h->beq_x, (size_t)E * 3) || dalloc(h, &h->beq_y, (size_t)E * 4) || dalloc(h, &h->state0, (size_t)E * 5)) return -1;
     // constant normal tables [survey Q8]: every key below derives from PRNGKey(0) only
     {
         const int S = d.S_in, dd = nm + 1, ne = d.n_el_in;
         float *z_init, *theta0, *zb, *ztmp;
         if (dalloc(h, &z_init, (size_t)B * NPAR) || dalloc(h, &theta0, (size_t)S * dd) || dalloc(h, &zb, (size_t)d.iters_in * (S - ne) * dd) ||
-            dalloc(h, &ztmp, (size_t)S * dd)) { mpcmmd_destroy(h); return -1; }
+            dalloc(h, &ztmp, (size_t)S * dd)) return -1;
         // host-side key derivation mirrors the device functions (integer-only Threefry)
         auto tf = [](uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o) {
             auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
@@ -256,50 +313,55 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
             k_normal_table<<<64, 256>>>(dk[0], dk[1], (S - ne) * dd, zb + (size_t)it * (S - ne) * dd);
         }
         float* zbT;
-        if (dalloc(h, &zbT, (size_t)d.iters_in * (S - ne) * dd)) { mpcmmd_destroy(h); return -1; }
+        if (dalloc(h, &zbT, (size_t)d.iters_in * (S - ne) * dd)) return -1;
         k_transpose_tables<<<64, 256>>>(zb, zbT, d.iters_in, S - ne, dd);
         float* th0T;
-        if (dalloc(h, &th0T, (size_t)S * dd)) { mpcmmd_destroy(h); return -1; }
+        if (dalloc(h, &th0T, (size_t)S * dd)) return -1;
         k_transpose_tables<<<64, 256>>>(theta0, th0T, 1, S, dd);
         d.z_init = z_init; d.theta0 = theta0; d.theta0T = th0T; d.zb_iter = zb; d.zb_iterT = zbT;
     }
-    // opt-in shared memory sizes
-    if (cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_SMEM_BYTES) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project smem opt-in failed"); }
-    if (cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ptc::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_project_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_project_tc smem opt-in failed"); }
+    // opt-in shared memory sizes (raise-only per (device, kernel): see raise_smem)
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (h->sm_count < 1) h->sm_count = 1;
+    if (raise_smem(device, (const void*)k_project, PROJ_SMEM_BYTES)) return fail("k_project smem opt-in failed");
+    if (raise_smem(device, (const void*)k_project_tc, ptc::SMEM_BYTES, true)) return fail("k_project_tc smem opt-in failed");
     {
-        size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(d, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(d, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
-        if (rs > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory"); }
-        if (rs > 48 * 1024 && (cudaFuncSetAttribute(k_rollouts<ROLL_OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess ||
-                               cudaFuncSetAttribute(k_rollouts<ROLL_FLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess ||
-                               cudaFuncSetAttribute(k_rollouts<ROLL_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs) != cudaSuccess)) { mpcmmd_destroy(h); return fail("k_rollouts smem opt-in failed"); }
+        size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(h, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(h, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
+        if (rs > 227 * 1024) return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory");
+        if (raise_smem(device, (const void*)k_rollouts<ROLL_OPT>, rs) || raise_smem(device, (const void*)k_rollouts<ROLL_FLY>, rs) ||
+            raise_smem(device, (const void*)k_rollouts<ROLL_STAGED>, rs)) return fail("k_rollouts smem opt-in failed");
     }
     {
         const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
         h->inner_mode = !mode ? 0 : !strcmp(mode, "warp") ? INNER_WARP : !strcmp(mode, "cta") ? INNER_CTA : !strcmp(mode, "generic") ? INNER_GENERIC :
-                        !strcmp(mode, "lat") ? INNER_CTA_LAT : 0;
+                        !strcmp(mode, "lat") ? INNER_CTA_LAT : !strcmp(mode, "split") ? INNER_SPLIT : !strcmp(mode, "pipe") ? INNER_PIPE : 0;
         if (!inner_cem_is_fast(d) && h->inner_mode != 0) h->inner_mode = INNER_GENERIC;
-        cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (inner_cem_is_fast(d)) {
+            const SplitKernels sk = split_kernels(d.nr);
+            if (raise_smem(device, (const void*)sk.eval, split_eval_smem(d)) || raise_smem(device, (const void*)sk.update, split_update_smem(d), true))
+                return fail("k_icem smem opt-in failed");
+            cudaFuncSetAttribute(sk.eval, cudaFuncAttributePreferredSharedMemoryCarveout, 50);     // 12 CTAs x 5.5 KB of operands, the rest stays L1
+            const char* mb = getenv("MPCMMD_PIPE_MINB");
+            if (mb) h->pipe_minb = atoi(mb);
+            if (raise_smem(device, (const void*)pipe_kernel(d.nr, h->pipe_minb), pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), true)) return fail("k_inner_cem_pipe smem opt-in failed");
+        }
         for (int kind = INNER_WARP; kind <= INNER_CTA_LAT; kind++) {
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
             inner_cem_fn f = inner_cem_kernel(d, kind);
             if (!f) continue;
             const size_t sm = inner_cem_smem_kind(d, kind);
-            if (sm > 227 * 1024) { mpcmmd_destroy(h); return fail("mpcmmd_create: reduced-set state does not fit in shared memory"); }
-            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { mpcmmd_destroy(h); return fail("k_inner_cem smem opt-in failed"); }
-            if (kind != INNER_GENERIC) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (sm > 227 * 1024) return fail("mpcmmd_create: reduced-set state does not fit in shared memory");
+            if (raise_smem(device, (const void*)f, sm, kind != INNER_GENERIC)) return fail("k_inner_cem smem opt-in failed");
             if (kind == INNER_WARP) {
-                int per_sm = 0, sms = 0;
+                int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-                h->warp_grid = per_sm * (sms > 0 ? sms : 1);
+                h->warp_grid = per_sm * h->sm_count;
             }
         }
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
-    *out = h;
     return 0;
 }
 
@@ -347,7 +409,10 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     }
     if (dalloc(h, &h->ridx, EB * d.nr)) return -1;
     if (inner_cem_is_fast(d) && dalloc(h, &h->bscratch, EB * d.S_in * (d.nr + 1))) return -1;
+    if (inner_cem_is_fast(d) && dalloc(h, &h->throws, EB * (d.nm + 1) * ICP_TH_LD)) return -1;
+    if (inner_cem_is_fast(d) && dalloc(h, &h->split_state, EB * split_layout(d.nr, d.S_in, d.n_el_in).total)) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
+    CK(cudaDeviceSynchronize());     // dalloc's memsets run on the legacy default stream; solves run on non-blocking streams that do not wait for it
     return 0;
 }
 // rollouts (+ risk for the num_reduced-rollout costs); mmd_opt continues with the inner CEM kernel.  Returns launches issued.
@@ -356,7 +421,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(d, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch; ra.ctrl = h->ctrl; ra.write_rolls = 0; ra.stage_ctrl = roll_stage_ctrl(d, r.cost_kind, r.n_samples);
+    ra.r = r; ra.spb = roll_spb(h, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch; ra.ctrl = h->ctrl; ra.write_rolls = 0; ra.stage_ctrl = roll_stage_ctrl(h, r.cost_kind, r.n_samples);
     inner_cem_fn f = nullptr;
     int kind = INNER_GENERIC;
     if (opt) {
@@ -364,13 +429,17 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         // (MPCMMD_INNER_CEM=warp): measured 233 ms vs 209 ms per 200-episode mmd_opt solve on B200 (profiles/r01_v7_summary.md) --
         // 19 independent instruction streams per SM thrash the 32 KB instruction cache.
         // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the build with the 96-register budget
-        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 9 * h->sm_count ? INNER_CTA_LAT : INNER_CTA);
+        // a launch of at most 3 chains per SM (one episode = 100 chains) is pure dependency latency: the latency build of the fused kernel
+        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 3 * h->sm_count ? INNER_CTA_LAT : INNER_DEFAULT_THROUGHPUT);
+        if (kind == INNER_PIPE && !pipe_ok(d)) kind = INNER_CTA;
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
-        f = inner_cem_kernel(d, kind);
-        if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10");
+        if (kind != INNER_SPLIT && kind != INNER_PIPE) {
+            f = inner_cem_kernel(d, kind);
+            if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,7,8,9,10");
+        }
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
-        if (kind != INNER_CTA && kind != INNER_CTA_LAT) {          // these kernels evaluate the risk themselves from the stored mother rollouts
+        if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
             if (!h->rolls_x) return fail("internal: mother-rollout scratch not allocated");
             ra.write_rolls = 1; ra.xroll = h->rolls_x; ra.yroll = h->rolls_y;
         }
@@ -382,7 +451,25 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         else k_rollouts<ROLL_FLY><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
     }
     if (n_launch) *n_launch = 1;
-    if (opt) {
+    if (opt && kind == INNER_PIPE) {
+        pipe_kernel(d.nr, h->pipe_minb)<<<(r.n_samples + 1) / 2, ICP_THREADS, pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), s>>>(d, ra, h->throws);
+        { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
+        if (n_launch) *n_launch = 3;
+    } else if (opt && kind == INNER_SPLIT) {
+        const SplitKernels sk = split_kernels(d.nr);
+        SplitArgs sa;
+        sa.n_chains = r.n_samples; sa.g0 = 0; sa.state = h->split_state; sa.feat = h->feat; sa.bscratch = h->bscratch;
+        sa.beta = r.beta; sa.sigma = r.sigma; sa.res_beta = r.res_beta; sa.ridx = h->ridx;
+        const long long nd = (long long)r.n_samples * d.nm * d.nm;
+        sk.dist<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(d, sa);
+        const size_t se = split_eval_smem(d), su = split_update_smem(d);
+        for (int it = 0; it < d.iters_in; it++) {
+            sk.eval<<<r.n_samples, (it == 0 && d.S_in > ICE_THREADS) ? 128 : ICE_THREADS, se, s>>>(d, sa, it);
+            sk.update<<<(r.n_samples + ICU_WARPS - 1) / ICU_WARPS, ICU_WARPS * 32, su, s>>>(d, sa, it);
+        }
+        { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
+        if (n_launch) *n_launch = 3 + 2 * d.iters_in;
+    } else if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
         if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
         else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
@@ -439,11 +526,12 @@ static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* ou
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
     int rc = enqueue_solve(h, kind, n_ep, h->own_stream, &launches);
     cudaError_t ce = cudaStreamEndCapture(h->own_stream, &g);
-    if (rc) return -1;
+    if (rc) { if (ce == cudaSuccess && g) cudaGraphDestroy(g); return -1; }
     CK(ce);
     cudaGraphExec_t ge;
-    CK(cudaGraphInstantiate(&ge, g, 0));
+    ce = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
+    CK(ce);
     h->graphs[key] = ge;
     h->graph_launches[key] = launches;
     h->last_launches = launches;
@@ -500,6 +588,21 @@ extern "C" int mpcmmd_solve_host(mpcmmd_handle h, int cost_kind, int n_ep, const
     return 0;
 }
 extern "C" int mpcmmd_last_launch_count(mpcmmd_handle h) { return h ? h->last_launches : 0; }
+extern "C" const char* mpcmmd_inner_cem_path(mpcmmd_handle h) {
+    if (!h) return "";
+    if (!inner_cem_is_fast(h->d)) return "k_inner_cem (generic, one CTA per chain)";
+    switch (h->inner_mode) {
+        case INNER_WARP: return "k_inner_cem_warp (one warp per chain, persistent)";
+        case INNER_CTA: return "k_inner_cem_fast (one CTA per chain)";
+        case INNER_PIPE: return "k_inner_cem_pipe (two chains per CTA: 3 evaluation warps + 1 serial warp, pipelined)";
+        case INNER_SPLIT: return "phase-split: k_icem_dist + 20 x (k_icem_eval + k_icem_update)";
+        case INNER_CTA_LAT: return "k_inner_cem_fast<LAT> (one CTA per chain, latency build)";
+        case INNER_GENERIC: return "k_inner_cem (generic, one CTA per chain)";
+        default: return INNER_DEFAULT_THROUGHPUT == INNER_PIPE
+                            ? "k_inner_cem_pipe (two chains per CTA: 3 evaluation warps + 1 serial warp); launches of <= 3 chains per SM: k_inner_cem_fast<LAT>"
+                            : "k_inner_cem_fast (one CTA per chain); launches of <= 3 chains per SM: its latency build";
+    }
+}
 
 // Re-run the solve of the inputs staged by the previous mpcmmd_solve* call WITHOUT the graph, with a CUDA event after
 // every launch on the launching stream, and return the device time per kernel class:
@@ -694,5 +797,58 @@ extern "C" int mpcmmd_fp32_peak(int device, float* tflops, int* sm_count) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
     *tflops = best;
     if (sm_count) *sm_count = prop.multiProcessorCount;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// XU / special-function peaks of this device, measured (SURVEY.md section 8d asks for an `ex2` peak next to the FP32-FMA one): the denominators
+// for the kernels whose hot instructions are MUFU (ex2.approx) or the IEEE division / square root sequences (MUFU.RCP / MUFU.RSQ + Newton
+// steps on the FMA pipe) -- k_rollouts' obstacle indicator divides twice per (point, obstacle), the bicycle step takes one sqrt.
+// out[0] = ex2.approx.ftz.f32 Gop/s, out[1] = div.rn.f32 Gop/s, out[2] = sqrt.rn.f32 Gop/s (thread-level operations per second / 1e9).
+template <int OP>
+__global__ void __launch_bounds__(256) k_xu_peak(float* out, int iters, float a) {
+    float x0 = 0.5f + threadIdx.x * 1e-4f, x1 = x0 + 0.01f, x2 = x0 + 0.02f, x3 = x0 + 0.03f, x4 = x0 + 0.04f, x5 = x0 + 0.05f, x6 = x0 + 0.06f, x7 = x0 + 0.07f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (OP == 0) {
+#define XU_EX2(v) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(-v))
+                XU_EX2(x0); XU_EX2(x1); XU_EX2(x2); XU_EX2(x3); XU_EX2(x4); XU_EX2(x5); XU_EX2(x6); XU_EX2(x7);
+#undef XU_EX2
+            } else if (OP == 1) {
+                x0 = __fdiv_rn(a, x0); x1 = __fdiv_rn(a, x1); x2 = __fdiv_rn(a, x2); x3 = __fdiv_rn(a, x3);
+                x4 = __fdiv_rn(a, x4); x5 = __fdiv_rn(a, x5); x6 = __fdiv_rn(a, x6); x7 = __fdiv_rn(a, x7);
+            } else {
+                x0 = __fsqrt_rn(x0 + a); x1 = __fsqrt_rn(x1 + a); x2 = __fsqrt_rn(x2 + a); x3 = __fsqrt_rn(x3 + a);
+                x4 = __fsqrt_rn(x4 + a); x5 = __fsqrt_rn(x5 + a); x6 = __fsqrt_rn(x6 + a); x7 = __fsqrt_rn(x7 + a);
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+extern "C" int mpcmmd_xu_peaks(int device, float* gops /* [3] */) {
+    if (!gops) return fail("mpcmmd_xu_peaks: null pointer");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 512;
+    float* buf; CK(cudaMalloc(&buf, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int op = 0; op < 3; op++) {
+        float best = 0.0f;
+        for (int rep = 0; rep < 5; rep++) {
+            CK(cudaEventRecord(e0));
+            if (op == 0) k_xu_peak<0><<<blocks, threads>>>(buf, iters, 1.25f);
+            else if (op == 1) k_xu_peak<1><<<blocks, threads>>>(buf, iters, 1.25f);
+            else k_xu_peak<2><<<blocks, threads>>>(buf, iters, 1.25f);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.0f; CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = 8.0 * 8 * (double)iters * blocks * threads;
+            const float g = (float)(ops / (ms * 1e-3) / 1e9);
+            if (rep > 0 && g > best) best = g;
+        }
+        gops[op] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
     return 0;
 }

@@ -175,6 +175,10 @@ class CEM:
                                             xo.ctypes.data, yo.ctypes.data, vd.ctypes.data, C.byref(o)))
         return out
 
+    def inner_cem_path(self) -> str:
+        """name of the reduced-set inner-CEM kernel path a throughput-sized mmd_opt launch of this handle takes (reporting only)"""
+        return self._lib.mpcmmd_inner_cem_path(self._h).decode()
+
     def last_launch_count(self) -> int:
         return int(self._lib.mpcmmd_last_launch_count(self._h))
 
@@ -310,3 +314,11 @@ def fp32_peak(device=0):
     tf = C.c_float(); sm = C.c_int()
     B.check(lib.mpcmmd_fp32_peak(int(device), C.byref(tf), C.byref(sm)))
     return float(tf.value), int(sm.value)
+
+
+def xu_peaks(device=0):
+    """dict(ex2_gops, div_gops, sqrt_gops): measured MUFU.EX2 / IEEE division / IEEE square-root throughput (thread-level Gop/s)."""
+    lib = B.load()
+    g = (C.c_float * 3)()
+    B.check(lib.mpcmmd_xu_peaks(int(device), g))
+    return dict(ex2_gops=float(g[0]), div_gops=float(g[1]), sqrt_gops=float(g[2]))

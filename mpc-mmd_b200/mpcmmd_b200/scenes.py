@@ -95,14 +95,19 @@ def static_batch(prob, episodes, variant="static"):
             x, y, _ = prob.cem_helper.compute_obs_trajectories(*sc)
         idx.append(i); xo.append(x); yo.append(y)
     E = len(idx)
+    if E == 0:                      # a rank whose shard is empty (more ranks than episodes) still takes part in the gather
+        xo = [np.zeros((0, prob.num_obs, NUM), F32)]; yo = [np.zeros((0, prob.num_obs, NUM), F32)]
+        return dict(idx_mpc=np.zeros(0, np.int32), init_state=np.zeros((0, 6), F32), mean_param=np.zeros((0, 8), F32), cov_param=np.zeros((0, 8, 8), F32),
+                    x_obs_traj=xo[0], y_obs_traj=yo[0], v_des=np.zeros(0, F32))
     return dict(idx_mpc=np.asarray(idx, np.int32), init_state=np.repeat(init_state[None], E, 0), mean_param=np.repeat(mean[None], E, 0),
                 cov_param=np.repeat(cov[None], E, 0), x_obs_traj=np.stack(xo).astype(F32), y_obs_traj=np.stack(yo).astype(F32),
                 v_des=np.full(E, v_des, F32))
 
 
-def flops_per_sample(cost: str, num_reduced: int, num_prime: int, num_obs: int, num_samples_cem=100, maxiter_beta_cem=20):
+def flops_per_sample(cost: str, num_reduced: int, num_prime: int, num_obs: int, num_samples_cem=100, maxiter_beta_cem=20, survey_count=False):
     """Algorithmic FLOPs (FMA = 2) of ONE CEM sample in ONE outer iteration, split by kernel -- the minimal formulation of
-    SURVEY.md section 8(d).  Returns dict(project=..., risk=...)."""
+    SURVEY.md section 8(d).  Returns dict(project=..., risk=...).  `survey_count=True` reproduces SURVEY's figure literally (S evaluations in every
+    inner iteration); the default counts what the algorithm needs: the elites keep their cost, so S + (iters - 1)(S - ne) rows are evaluated."""
     from math import log2
     nr, np_, O, S, T, n = num_reduced, num_prime, num_obs, num_samples_cem, 100, 11
     nm = nr * nr
@@ -113,8 +118,12 @@ def flops_per_sample(cost: str, num_reduced: int, num_prime: int, num_obs: int, 
     f_fit = 2 * nm * (2 * np_ * n + 2 * n * n) if opt else 0
     f_rs = 0
     if opt:
-        per_it = S * (2 * nm * log2(nm) + 2 * (nr * nr + nr * nm) + nr * nm + (2.0 / 3.0) * (nr + 1) ** 3 + 2 * (nr + 1) ** 2 + 2 * nr * nr + 2 * nr) \
-            + 2 * S * log2(S) + 11 * (nm + 1) ** 2 + (nm + 1) ** 3 / 3.0 + 89 * (nm + 1) ** 2
-        f_rs = 33 * nm * nm + maxiter_beta_cem * per_it
+        ne = max(int(0.1 * S) + 1, 3)                       # compute_beta.py:26
+        f_eval = 2 * nm * log2(nm) + 2 * (nr * nr + nr * nm) + nr * nm + (2.0 / 3.0) * (nr + 1) ** 3 + 2 * (nr + 1) ** 2 + 2 * nr * nr + 2 * nr
+        f_upd = 2 * S * log2(S) + ne * (nm + 1) ** 2 + (nm + 1) ** 3 / 3.0 + (S - ne) * (nm + 1) ** 2
+        # the elites keep their cost from the iteration that produced them (same row => same value), so only the S - ne resampled rows
+        # are evaluated after iteration 0: S + (iters - 1) (S - ne) evaluations, not iters * S
+        n_eval = maxiter_beta_cem * S if survey_count else S + (maxiter_beta_cem - 1) * (S - ne)
+        f_rs = 33 * nm * nm + n_eval * f_eval + maxiter_beta_cem * f_upd
     f_cost = 8 * nr * O * np_ + 5 * nr * nr + 3 * nr
     return dict(project=float(f_guess + f_proj + f_ctrl), risk=float(f_roll + f_fit + f_rs + f_cost))

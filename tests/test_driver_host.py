@@ -141,3 +141,18 @@ def test_assemble_dynamic_schema(driver):
     assert arrays["x_obs_traj"].shape == (3, 3, 100) and arrays["psi_obs"].shape == (3, 3)
     assert arrays["init_state"][0].tolist() == [0.0, -1.75, 5.0, 0.0, 0.0, 0.0]                                    # D/main_mpc.py:34-42
     assert arrays["cx"][:, 0].tolist() == [1.0, 2.0, 4.0]
+
+
+def test_empty_shard_when_more_ranks_than_episodes(driver):
+    """WORLD_SIZE > --num_configs: a rank with no episodes builds correctly shaped empty inputs / records instead of crashing before the gather"""
+    from mpcmmd_b200 import scenes
+
+    class _P:
+        num_obs = 4
+    assert driver.shard(3, 5, 8) == []
+    b = scenes.static_batch(_P, [], "static")
+    assert b["idx_mpc"].shape == (0,) and b["x_obs_traj"].shape == (0, 4, 100) and b["cov_param"].shape == (0, 8, 8)
+    rec = driver.pack_records([], dict(cost_obs=np.zeros(0, f32), cost_lane=np.zeros(0, f32), cx=np.zeros((0, 11), f32), cy=np.zeros((0, 11), f32)))
+    assert rec.shape == (0, 26)
+    full = np.concatenate([rec, driver.pack_records([0, 1, 2], _fake_out([0, 1, 2]))], 0)
+    assert driver.assemble(full, 4, 1e-5)["cx"][:, 0].tolist() == [1.0, 2.0]
