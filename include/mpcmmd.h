@@ -154,6 +154,17 @@ int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const float *acc, c
                       const float *z1, const float *z2, const float *z3, const uint32_t *keys,
                       const float *x_obs, const float *y_obs, float *risk, float *lane, float *beta, float *sigma, float *res_beta);
 
+/* The same stage with the random draws of the beta noise model INJECTED as tensors (SURVEY.md section 7 hard part 1 / 8b `set_noise`):
+ * beta_acc, beta_steer (n, nr*np) are the samples of jax.random.beta(key, 2|u|, 5|u|) at cem_helper.py:427 / :432 (:492 / :497) for every
+ * sample's own controls, z3 (nr*np) the common-mode normals.  No device RNG runs, so a machine that has the reference's jax==0.3.23 can feed
+ * its own draws and compare everything downstream of the sampler.  (Gaussian noise: mpcmmd_stage_risk already takes z1, z2, z3.) */
+int mpcmmd_stage_risk_injected(mpcmmd_handle h, int cost_kind, int n, const float *acc, const float *steer, const float *state0,
+                               const float *z3, const float *beta_acc, const float *beta_steer, const float *x_obs, const float *y_obs,
+                               float *risk, float *lane, float *beta, float *sigma, float *res_beta);
+
+/* initial CEM batch of one episode (Helper.sampling_param, cem_helper.py:122-150): mean (8), cov (64) -> params (B,8). */
+int mpcmmd_stage_init(mpcmmd_handle h, const float *mean, const float *cov, float *params);
+
 /* elite selection + mean/cov update + resampling for one episode (cem.py:233-315, cem_helper.py:264-314).
  * params (B,8) is replaced by the next batch; mean (8), cov (64) updated in place; z_cem (B-5,8); sel (1) int32. */
 int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float *res_norm, const float *risk, const float *cost_base,

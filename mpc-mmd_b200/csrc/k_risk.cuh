@@ -23,6 +23,7 @@ struct RiskArgs {
     size_t key_stride;
     const float* btab;               // episode e at btab + e*btab_stride: [4][GT_FIELDS][nr*np] (beta noise; null -> direct sampler)
     size_t btab_stride;
+    const float *binj1, *binj2;      // [n][nr*np] injected Beta draws (acceleration, steering) instead of the device sampler; null in solves (mpcmmd_stage_risk_injected)
     const float *x_obs, *y_obs;      // [E][O][100]
     float *risk, *lane;              // [n]
     float *beta, *sigma, *res_beta;  // [n][nr], [n], [n][iters_in]
@@ -171,7 +172,9 @@ __device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, 
         const uint32_t* keys = a.keys + e * a.key_stride;
         dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
         float b1, b2;
-        if (a.btab) {
+        if (a.binj1) {
+            b1 = a.binj1[(size_t)g * n + el]; b2 = a.binj2[(size_t)g * n + el];
+        } else if (a.btab) {
             const float* bt = a.btab + e * a.btab_stride;
             b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
             b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));

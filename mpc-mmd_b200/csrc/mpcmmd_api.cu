@@ -173,7 +173,9 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
         case 4: return k_inner_cem<4>;
         case 5: return k_inner_cem<5>;
         case 6: return k_inner_cem<6>;
+        case 7: return k_inner_cem<7>;
         case 8: return k_inner_cem<8>;
+        case 9: return k_inner_cem<9>;
         case 10: return k_inner_cem<10>;
         default: return nullptr;
     }
@@ -195,7 +197,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     if (B < cfg->ellite_num_cost || cfg->ellite_num_cost > 32 || cfg->ellite_num > 8 || cfg->ellite_num > cfg->ellite_num_cost)
         return fail("mpcmmd_create: need ellite_num <= 8, ellite_num <= ellite_num_cost <= min(32, num_batch)");
     if (np < 2 || np > MPCMMD_T) return fail("mpcmmd_create: num_prime must be in [2,100]");
-    if (nr < 2 || nr > MPCMMD_MAX_NR_DEV) return fail("mpcmmd_create: num_reduced must be in [2,64] (mmd_opt: one of 2,3,4,5,6,8,10)");
+    if (nr < 2 || nr > MPCMMD_MAX_NR_DEV) return fail("mpcmmd_create: num_reduced must be in [2,64] (mmd_opt: 2..10)");
     if (cfg->num_obs < 1 || E < 1) return fail("mpcmmd_create: num_obs and max_episodes must be >= 1");
     if (cfg->num_samples_cem > RISKO_THREADS * 8 || cfg->num_ellite_beta < 2 || cfg->num_ellite_beta >= cfg->num_samples_cem)
         return fail("mpcmmd_create: bad inner-CEM sizes");
@@ -399,7 +401,7 @@ static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s)
 // mother rollouts / features scratch of the mmd_opt path, allocated on first use ([E*B][nm][np] x2 and [E*B][nm][22])
 static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (h->xroll) return 0;
-    if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,8,10 (larger reduced sets: cvar / saa / mmd_random only)");
+    if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be 2..10 (larger reduced sets: cvar / saa / mmd_random only)");
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
     if (dalloc(h, &h->feat, EB * d.nm * 2 * NV) || dalloc(h, &h->ctrl, EB * 2 * d.nr * d.np)) return -1;
     // the mother rollouts are stored only for the kernels that read them back (generic / warp-per-chain); allocated on first such launch
@@ -435,7 +437,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
         if (kind != INNER_SPLIT && kind != INNER_PIPE) {
             f = inner_cem_kernel(d, kind);
-            if (!f) return fail("mmd_opt: num_reduced must be one of 2,3,4,5,6,7,8,9,10");
+            if (!f) return fail("mmd_opt: num_reduced must be in [2, 10]");
         }
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
@@ -500,7 +502,7 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
         r.n_samples = n_ep * d.B; r.B = d.B; r.cost_kind = kind; r.acc = w.acc; r.steer = w.steer; r.state0 = h->state0;
         r.z1 = w.z1 + it * n; r.z2 = w.z2 + it * n; r.z3 = w.z3 + it * n; r.z_stride = (size_t)d.iters * n;
         r.keys = w.keys + it * 4; r.key_stride = (size_t)d.iters * 4;
-        r.btab = w.btab ? w.btab + (size_t)it * 4 * GT_FIELDS * n : nullptr; r.btab_stride = (size_t)d.iters * 4 * GT_FIELDS * n;
+        r.btab = w.btab ? w.btab + (size_t)it * 4 * GT_FIELDS * n : nullptr; r.btab_stride = (size_t)d.iters * 4 * GT_FIELDS * n; r.binj1 = r.binj2 = nullptr;
         r.x_obs = w.x_obs; r.y_obs = w.y_obs; r.risk = w.risk; r.lane = w.lane; r.beta = w.beta; r.sigma = w.sigma; r.res_beta = w.res_beta;
         int nl = 0;
         if (launch_risk(h, r, s, &nl)) return -1;
@@ -675,18 +677,34 @@ extern "C" int mpcmmd_stage_project(mpcmmd_handle h, int n, const float* params,
     CK(cudaDeviceSynchronize());
     return 0;
 }
-extern "C" int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const float* acc, const float* steer, const float* state0,
-                                 const float* z1, const float* z2, const float* z3, const uint32_t* keys, const float* x_obs, const float* y_obs,
-                                 float* risk, float* lane, float* beta, float* sigma, float* res_beta) {
+static int stage_risk_impl(mpcmmd_handle h, int cost_kind, int n, const float* acc, const float* steer, const float* state0,
+                           const float* z1, const float* z2, const float* z3, const uint32_t* keys, const float* binj1, const float* binj2,
+                           const float* x_obs, const float* y_obs, float* risk, float* lane, float* beta, float* sigma, float* res_beta) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
     RiskArgs r;
     r.n_samples = n; r.B = n; r.cost_kind = cost_kind; r.acc = acc; r.steer = steer; r.state0 = state0; r.z1 = z1; r.z2 = z2; r.z3 = z3; r.z_stride = 0;
-    r.keys = keys; r.key_stride = 0; r.btab = nullptr; r.btab_stride = 0; r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
+    r.keys = keys; r.key_stride = 0; r.btab = nullptr; r.btab_stride = 0; r.binj1 = binj1; r.binj2 = binj2;
+    r.x_obs = x_obs; r.y_obs = y_obs; r.risk = risk; r.lane = lane; r.beta = beta; r.sigma = sigma; r.res_beta = res_beta;
     if (cost_kind == MPCMMD_COST_MMD_OPT && ensure_opt_scratch(h)) return -1;
     if (launch_risk(h, r, 0)) return -1;
     CK(cudaDeviceSynchronize());
     return 0;
+}
+extern "C" int mpcmmd_stage_risk(mpcmmd_handle h, int cost_kind, int n, const float* acc, const float* steer, const float* state0,
+                                 const float* z1, const float* z2, const float* z3, const uint32_t* keys, const float* x_obs, const float* y_obs,
+                                 float* risk, float* lane, float* beta, float* sigma, float* res_beta) {
+    return stage_risk_impl(h, cost_kind, n, acc, steer, state0, z1, z2, z3, keys, nullptr, nullptr, x_obs, y_obs, risk, lane, beta, sigma, res_beta);
+}
+// the same stage with the random draws of the beta noise model INJECTED: beta_acc / beta_steer (n, nr*np) are the samples of
+// jax.random.beta(key, 2|u|, 5|u|) at cem_helper.py:427 / :432 (:492 / :497), z3 (nr*np) the common-mode normals.  No device RNG runs.
+extern "C" int mpcmmd_stage_risk_injected(mpcmmd_handle h, int cost_kind, int n, const float* acc, const float* steer, const float* state0,
+                                          const float* z3, const float* beta_acc, const float* beta_steer, const float* x_obs, const float* y_obs,
+                                          float* risk, float* lane, float* beta, float* sigma, float* res_beta) {
+    if (!h) return fail("null handle");
+    if (h->d.noise_kind != 1) return fail("mpcmmd_stage_risk_injected: the handle was not created with beta noise (gaussian draws are injected through mpcmmd_stage_risk's z1, z2, z3)");
+    if (!beta_acc || !beta_steer || !z3) return fail("mpcmmd_stage_risk_injected: null draw tensor");
+    return stage_risk_impl(h, cost_kind, n, acc, steer, state0, z3, z3, z3, (const uint32_t*)h->w.keys, beta_acc, beta_steer, x_obs, y_obs, risk, lane, beta, sigma, res_beta);
 }
 extern "C" int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float* res_norm, const float* risk, const float* cost_base, float* params,
                                    float* mean, float* cov, const float* z_cem, int32_t* sel) {
@@ -701,6 +719,19 @@ extern "C" int mpcmmd_stage_select(mpcmmd_handle h, int cost_kind, const float* 
     a.o_sel = sel; a.sel_stride = 1;
     k_select<<<1, d.B <= SEL_RANK_MAX ? SEL_THREADS : SEL_THREADS_BIG, sel_smem(d)>>>(d, a);
     CK(cudaDeviceSynchronize());
+    return 0;
+}
+// the initial CEM batch of one episode (Helper.sampling_param, cem_helper.py:122-150): k_init on (mean, cov), all DEVICE pointers
+extern "C" int mpcmmd_stage_init(mpcmmd_handle h, const float* mean, const float* cov, float* params) {
+    if (!h) return fail("null handle");
+    if (!mean || !cov || !params) return fail("mpcmmd_stage_init: null pointer");
+    CK(cudaSetDevice(h->device));
+    const DCfg& d = h->d; DWork& w = h->w;
+    CK(cudaMemcpy(w.mean0, mean, sizeof(float) * NPAR, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(w.cov0, cov, sizeof(float) * 64, cudaMemcpyDeviceToDevice));
+    k_init<<<1, d.B <= SEL_RANK_MAX ? 128 : 1024>>>(d, w, 1);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(params, w.params, sizeof(float) * d.B * NPAR, cudaMemcpyDeviceToDevice));
     return 0;
 }
 extern "C" int mpcmmd_stage_noise(mpcmmd_handle h, int32_t idx_mpc, int32_t iter, float* z1, float* z2, float* z3, float* z_cem, uint32_t* keys) {

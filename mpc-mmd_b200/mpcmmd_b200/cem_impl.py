@@ -260,6 +260,29 @@ class CEM:
                                             o["risk"].data_ptr(), o["lane"].data_ptr(), o["beta"].data_ptr(), o["sigma"].data_ptr(), o["res_beta"].data_ptr()))
         return {k: v.cpu().numpy() for k, v in o.items()}
 
+    def stage_risk_injected(self, cost, acc, steer, state0, z3, beta_acc, beta_steer, x_obs_traj, y_obs_traj):
+        """risk stage with the beta-noise draws injected: beta_acc, beta_steer (n, nr*np) = the reference's jax.random.beta samples"""
+        torch = self._torch
+        a, s = self._t(acc), self._t(steer); n = a.shape[0]
+        st0, tz3 = self._t(state0), self._t(z3)
+        b1, b2 = self._t(np.asarray(beta_acc, F32).reshape(n, -1)), self._t(np.asarray(beta_steer, F32).reshape(n, -1))
+        xo, yo = self._t(x_obs_traj), self._t(y_obs_traj)
+        f = dict(device=self.device, dtype=torch.float32)
+        o = dict(risk=torch.empty(n, **f), lane=torch.empty(n, **f), beta=torch.zeros(n, self.num_reduced, **f), sigma=torch.zeros(n, **f),
+                 res_beta=torch.zeros(n, self.maxiter_beta_cem, **f))
+        B.check(self._lib.mpcmmd_stage_risk_injected(self._h, B.COST_KINDS[cost], n, a.data_ptr(), s.data_ptr(), st0.data_ptr(), tz3.data_ptr(),
+                                                     b1.data_ptr(), b2.data_ptr(), xo.data_ptr(), yo.data_ptr(), o["risk"].data_ptr(),
+                                                     o["lane"].data_ptr(), o["beta"].data_ptr(), o["sigma"].data_ptr(), o["res_beta"].data_ptr()))
+        return {k: v.cpu().numpy() for k, v in o.items()}
+
+    def stage_init(self, mean, cov):
+        """initial CEM batch (B,8) of `Helper.sampling_param` for (mean, cov)"""
+        torch = self._torch
+        m, cv = self._t(mean), self._t(np.asarray(cov, F32).reshape(-1))
+        out = torch.empty(self.num_batch, 8, device=self.device, dtype=torch.float32)
+        B.check(self._lib.mpcmmd_stage_init(self._h, m.data_ptr(), cv.data_ptr(), out.data_ptr()))
+        return out.cpu().numpy()
+
     def stage_select(self, cost, res_norm, risk, cost_base, params, mean, cov, z_cem):
         torch = self._torch
         p = self._t(params).clone(); m = self._t(mean).clone(); cv = self._t(np.asarray(cov, F32).reshape(-1)).clone()

@@ -81,7 +81,7 @@ class OSolveOut(C.Structure):
 
 
 class ONoise(C.Structure):
-    _fields_ = [("z1", FP), ("z2", FP), ("z3", FP), ("k1", C.c_uint32 * 2), ("k2", C.c_uint32 * 2)]
+    _fields_ = [("z1", FP), ("z2", FP), ("z3", FP), ("k1", C.c_uint32 * 2), ("k2", C.c_uint32 * 2), ("b1", FP), ("b2", FP)]
 
 
 class OSelectOut(C.Structure):
@@ -373,9 +373,14 @@ class OracleCEM:
         lib().oracle_noise_tables(C.byref(self.cfg), C.c_int32(int(idx_mpc)), C.c_int32(int(it)), _fp(z1), _fp(z2), _fp(z3), _fp(zc), keys)
         return z1, z2, z3, zc.reshape(-1, NPAR), [int(k) for k in keys]
 
-    def risk(self, cost, acc, steer, st0, noise, x_obs_traj, y_obs_traj, want_rollouts=False):
+    def risk(self, cost, acc, steer, st0, noise, x_obs_traj, y_obs_traj, want_rollouts=False, beta_draws=None):
+        """`beta_draws` = (b_acc, b_steer), each (nr, np): the two `jax.random.beta` samples of cem_helper.py:427-436 injected instead of drawn"""
         z1, z2, z3, _, keys = noise
-        nz = ONoise(_fp(z1), _fp(z2), _fp(z3), (C.c_uint32 * 2)(keys[0], keys[1]), (C.c_uint32 * 2)(keys[2], keys[3]))
+        b1 = b2 = None
+        if beta_draws is not None:
+            b1, b2 = (np.ascontiguousarray(b, f32).reshape(-1) for b in beta_draws)
+        nz = ONoise(_fp(z1), _fp(z2), _fp(z3), (C.c_uint32 * 2)(keys[0], keys[1]), (C.c_uint32 * 2)(keys[2], keys[3]),
+                    _fp(b1) if b1 is not None else None, _fp(b2) if b2 is not None else None)
         o = ORiskOut()
         acc = np.ascontiguousarray(acc, f32); steer = np.ascontiguousarray(steer, f32); st0 = np.ascontiguousarray(st0, f32)
         xo = np.ascontiguousarray(x_obs_traj, f32); yo = np.ascontiguousarray(y_obs_traj, f32)

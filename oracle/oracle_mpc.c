@@ -397,6 +397,8 @@ static float saa_cost(const ocfg_t *c, const float *v) {
 typedef struct {           /* per (episode, outer iteration) noise, shared by all B samples [Q5] */
     const float *z1, *z2, *z3;   /* (nr,np) normals: acc, steer, common-mode */
     okey_t k1, k2;               /* beta noise keys (cem_helper.py:427,432 / 492,497) */
+    const float *b1, *b2;        /* optional (nr,np): the two jax.random.beta draws themselves, INJECTED (NULL = draw them from k1 / k2).  Lets a machine
+                                    that has the reference's jax==0.3.23 feed its own samples and so take the restated sampler out of the comparison */
 } onoise_t;
 
 static void rollout_one(const ocfg_t *c, const float *a, const float *s, const float *st0, float *xr, float *yr) {
@@ -427,10 +429,10 @@ static void noisy_controls(const ocfg_t *c, const float *acc, const float *steer
         float *a = (float *)malloc(sizeof(float) * n), *b = (float *)malloc(sizeof(float) * n);
         float *smp = (float *)malloc(sizeof(float) * n);
         for (int r = 0; r < nr; r++) for (int t = 0; t < np; t++) { a[r * np + t] = c->beta_a * fabsf(acc[t]); b[r * np + t] = c->beta_b * fabsf(acc[t]); }
-        rng_beta(nz->k1, a, b, (size_t)n, smp);
+        if (nz->b1) memcpy(smp, nz->b1, sizeof(float) * n); else rng_beta(nz->k1, a, b, (size_t)n, smp);
         for (int i = 0; i < n; i++) pa[i] = c->sigma_acc * (2.0f * smp[i] - 1.0f);
         for (int r = 0; r < nr; r++) for (int t = 0; t < np; t++) { a[r * np + t] = c->beta_a * fabsf(steer[t]); b[r * np + t] = c->beta_b * fabsf(steer[t]); }
-        rng_beta(nz->k2, a, b, (size_t)n, smp);
+        if (nz->b2) memcpy(smp, nz->b2, sizeof(float) * n); else rng_beta(nz->k2, a, b, (size_t)n, smp);
         for (int i = 0; i < n; i++) ps[i] = c->ksig_steer * (2.0f * smp[i] - 1.0f);
         free(a); free(b); free(smp);
     }
@@ -778,7 +780,7 @@ int oracle_solve(const ocfg_t *c, int cost_kind, int32_t idx_mpc, const float *i
     for (int it = 0; it < c->iters; it++) {
         uint32_t keys[4];
         oracle_noise_tables(c, idx_mpc, it, z1, z2, z3, z_cem, keys);
-        onoise_t nz = {z1, z2, z3, {keys[0], keys[1]}, {keys[2], keys[3]}};
+        onoise_t nz = {z1, z2, z3, {keys[0], keys[1]}, {keys[2], keys[3]}, NULL, NULL};
         if (tr && tr->params) memcpy(tr->params + (size_t)it * B * NP_, params, sizeof(float) * B * NP_);
         if (tr && tr->mean) memcpy(tr->mean + it * NP_, mean, sizeof mean);
         if (tr && tr->cov) memcpy(tr->cov + it * NP_ * NP_, cov, sizeof cov);

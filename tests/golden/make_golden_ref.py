@@ -41,9 +41,15 @@ OPT_CASES = [
 ]
 
 
+REAL_JAX = os.environ.get("MPCMMD_GOLDEN_JAX", "shim") == "real"     # make_golden_jax.py: the reference on its OWN runtime (jax==0.3.23), no stand-in
+REF_ROOT = os.environ.get("MPCMMD_REFERENCE_ROOT", "/root/reference")
+OUT_NAME = "ref_stages_jax.npz" if REAL_JAX else "ref_stages.npz"
+
+
 def _setup(variant_dir):
-    sys.path.insert(0, os.path.join(HERE, "jax_shim"))
-    ref = os.path.join("/root/reference", variant_dir)
+    if not REAL_JAX:
+        sys.path.insert(0, os.path.join(HERE, "jax_shim"))
+    ref = os.path.join(REF_ROOT, variant_dir)
     sys.path.insert(1, ref)
     sys.path.insert(1, os.path.join(ref, "optimizer"))
     sys.path.insert(1, ROOT)
@@ -86,7 +92,11 @@ def run_case(name, variant_dir, args, cost, iters, keep):
     _record(prob.costs, ["compute_cvar_obs_vmap", "compute_cvar_lane_vmap", "compute_saa_obs_vmap", "compute_saa_lane_vmap",
                          "compute_mmd_obs_vmap"], log)
     prob.maxiter_cem = iters
-    out = getattr(prob, "compute_cem_" + cost)(idx, jnp.asarray(init_state), jnp.asarray(mean), np.asarray(cov, np.float64), xo, yo, v_des)
+    import contextlib
+    import jax
+    # real JAX: the solve is @jit-ed, so the stage hooks would see tracers; run it op by op instead (same XLA kernels, concrete arrays)
+    with (jax.disable_jit() if REAL_JAX else contextlib.nullcontext()):
+        out = getattr(prob, "compute_cem_" + cost)(idx, jnp.asarray(init_state), jnp.asarray(mean), np.asarray(cov, np.float64), xo, yo, v_des)
     g = {"meta.args": np.array([str(a) for a in args]), "meta.cost": np.array(cost), "meta.variant": np.array(variant), "meta.idx_mpc": np.array(idx),
          "meta.v_des": f32(v_des), "init_state": np.asarray(init_state, f32), "x_obs_traj": np.asarray(xo, f32), "y_obs_traj": np.asarray(yo, f32),
          "mean0": np.asarray(mean, f32), "cov0": np.asarray(cov, f32), "meta.iters": np.array(keep),
@@ -191,8 +201,11 @@ def main():
                 for k in z.files:
                     merged[c[0] + "/" + k] = z[k]
             os.remove(p)
-    np.savez_compressed(os.path.join(HERE, "ref_stages.npz"), **merged)
-    print("wrote ref_stages.npz: %d arrays, %.0f KB" % (len(merged), os.path.getsize(os.path.join(HERE, "ref_stages.npz")) / 1024))
+    if REAL_JAX:
+        import jax
+        merged["meta.jax_version"] = np.array(jax.__version__)
+    np.savez_compressed(os.path.join(HERE, OUT_NAME), **merged)
+    print("wrote %s: %d arrays, %.0f KB" % (OUT_NAME, len(merged), os.path.getsize(os.path.join(HERE, OUT_NAME)) / 1024))
 
 
 if __name__ == "__main__":

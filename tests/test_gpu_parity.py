@@ -223,7 +223,7 @@ def _controls(ora, rng, n):
 @pytest.mark.parametrize("cost,noise,nr,npr,nobs", [
     ("cvar", "gaussian", 5, 30, 2), ("cvar", "beta", 5, 50, 4), ("saa", "gaussian", 4, 20, 3), ("mmd_random", "gaussian", 5, 30, 2),
     ("mmd_opt", "gaussian", 5, 30, 2), ("mmd_opt", "beta", 3, 20, 2), ("mmd_opt", "gaussian", 10, 40, 3), ("cvar", "gaussian", 10, 100, 6),
-    ("mmd_opt", "beta", 6, 30, 2), ("mmd_opt", "gaussian", 8, 25, 3)])
+    ("mmd_opt", "beta", 6, 30, 2), ("mmd_opt", "gaussian", 8, 25, 3), ("mmd_opt", "gaussian", 7, 20, 2), ("mmd_opt", "beta", 9, 20, 2)])
 def test_stage_risk_bit_exact(mods, cost, noise, nr, npr, nobs):
     kw = dict(num_samples_cem=40, maxiter_beta_cem=4) if cost == "mmd_opt" else {}
     prob, ora = _pair(mods, (nr, nobs, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), **kw)
@@ -245,6 +245,58 @@ def test_stage_risk_bit_exact(mods, cost, noise, nr, npr, nobs):
         if cost == "mmd_opt":
             _eq(got["res_beta"][i], ref["res_beta"], "res_beta")
     assert np.any(got["risk"] != got["risk"][0]) or cost == "saa"
+
+
+@pytest.mark.parametrize("cost,nr,npr", [("cvar", 5, 50), ("mmd_opt", 5, 30), ("mmd_random", 4, 20)])
+def test_stage_risk_injected_beta_draws(mods, cost, nr, npr):
+    """beta noise with the two jax.random.beta samples of cem_helper.py:427-436 INJECTED as tensors (mpcmmd_stage_risk_injected): no device RNG
+    runs, CUDA and oracle consume the same draws and must agree bit for bit downstream of the sampler (rollouts, reduced-set CEM, risk).  This
+    is the entry a machine with the reference's own jax==0.3.23 uses to take the restated Marsaglia-Tsang sampler out of the comparison."""
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=4) if cost == "mmd_opt" else {}
+    prob, ora = _pair(mods, (nr, 3, 0.3, npr, "beta", 0.05, 0.01), **kw)
+    rng = np.random.default_rng(29)
+    n = 7
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(99, 1)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(3, 4)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    xo = xo.copy(); xo[0] = np.linspace(2, 60, 100); yo = yo.copy(); yo[0] = 1.75
+    # any draws in (0, 1) do: here NumPy's Beta(2|u|, 5|u|) on the sample's own controls (|u| floored: NumPy rejects a = 0)
+    b_acc = np.stack([rng.beta(2 * np.maximum(np.abs(acc[i][:npr]), 1e-3), 5 * np.maximum(np.abs(acc[i][:npr]), 1e-3), (nr, npr)) for i in range(n)]).astype(f32)
+    b_steer = np.stack([rng.beta(2 * np.maximum(np.abs(steer[i][:npr]), 1e-3), 5 * np.maximum(np.abs(steer[i][:npr]), 1e-3), (nr, npr)) for i in range(n)]).astype(f32)
+    got = prob.stage_risk_injected(cost, acc, steer, st0, noise_t[2], b_acc, b_steer, xo, yo)
+    plain = prob.stage_risk(cost, acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk(cost, acc[i], steer[i], st0, noise_t, xo, yo, beta_draws=(b_acc[i], b_steer[i]))
+        _eq(got["risk"][i], ref["risk"], f"risk[{i}]"); _eq(got["lane"][i], ref["lane"], f"lane[{i}]")
+        if cost == "mmd_opt":
+            _eq(got["beta"][i], ref["beta"], "beta"); _eq(got["sigma"][i], ref["sigma"], "sigma"); _eq(got["res_beta"][i], ref["res_beta"], "res_beta")
+    assert np.isfinite(got["risk"]).all()
+    if cost == "mmd_opt":
+        assert not np.array_equal(got["res_beta"], plain["res_beta"])          # the injected draws really replaced the device sampler's
+
+
+def test_two_handles_with_different_inner_sizes_alternate(mods):
+    """two live handles on one device whose inner-CEM kernels need different amounts of dynamic shared memory (same kernel, same num_reduced):
+    the opt-in limit is per (device, kernel) and must only ever be raised (a second, smaller handle used to lower it)"""
+    cem_impl, O = mods
+    args = (5, 2, 0.1, 30, "gaussian", 0.02, 0.01)
+    big = dict(num_batch=24, maxiter_cem=2, num_samples_cem=100, maxiter_beta_cem=3)
+    small = dict(num_batch=24, maxiter_cem=2, num_samples_cem=40, maxiter_beta_cem=3)
+    pb = cem_impl.CEM(*args, max_episodes=2, **big)
+    ps = cem_impl.CEM(*args, max_episodes=2, **small)          # created AFTER the big one
+    ob, os_ = O.OracleCEM(*args, **big), O.OracleCEM(*args, **small)
+    init_state, mean, cov, v_des = O.driver_inputs("static")
+    idx, xo, yo = _episodes(O, ob, 2, 2)
+    stack = lambda a: np.stack([a] * 2)
+    for rnd in range(2):
+        for prob, ora in ((pb, ob), (ps, os_), (pb, ob)):
+            got = prob.solve_batch("mmd_opt", idx, stack(init_state), stack(mean), stack(cov), xo, yo, [v_des] * 2)
+            if rnd == 0:
+                ref = ora.solve("mmd_opt", idx[0], init_state, mean, cov, xo[0], yo[0], v_des)
+                for k in ("cx", "cy", "cost_obs", "res_beta"):
+                    _eq(got[k][0], ref[k], f"S={prob.num_samples_cem} {k}")
 
 
 def test_stage_select_bit_exact(mods):

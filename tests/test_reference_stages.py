@@ -14,7 +14,10 @@ import numpy as np
 import pytest
 
 f32 = np.float32
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_stages.npz")
+GDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = os.path.join(GDIR, "ref_stages.npz")
+# fixtures recorded with the reference's own runtime (real jax==0.3.23, tests/golden/make_golden_jax.py): used in addition when present
+GOLD_FILES = ["ref_stages.npz"] + (["ref_stages_jax.npz"] if os.path.exists(os.path.join(GDIR, "ref_stages_jax.npz")) else [])
 TOL = 1e-4
 
 CASES = ["A_static_gauss_cvar", "B_static_beta_cvar", "C_dynamic_gauss_cvar", "D_static_gauss_saa", "E_static_gauss_mmd_random"]
@@ -34,9 +37,9 @@ class Case:
         return self.d[k]
 
 
-@pytest.fixture(scope="module")
-def gold():
-    with np.load(GOLD) as z:
+@pytest.fixture(scope="module", params=GOLD_FILES)
+def gold(request):
+    with np.load(os.path.join(GDIR, request.param)) as z:
         return {n: Case(z, n) for n in CASES + OPT_CASES}
 
 
@@ -92,9 +95,7 @@ class CudaImpl:
         return self.p.tables()[0]
 
     def sample_params(self, mean, cov, z):
-        # the C ABI samples inside k_init / k_select; exercise it through stage_select with a degenerate elite update is not
-        # equivalent, so the initial batch is checked through a 0-iteration-equivalent: table + host Cholesky is oracle-side only
-        return None
+        return self.p.stage_init(mean, cov)          # k_init: Cholesky of cov + the constant normal table (= z) + speed clip, cem_helper.py:122-150
 
     def project(self, params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane):
         return self.p.stage_project(params, beq_x, beq_y, v_des, lam_x, lam_y, s_lane)
