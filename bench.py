@@ -373,7 +373,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- the other BASELINE workloads and the weak-scaled value, device-resident, same timing rules (extra keys; not the headline)
-    extras, weak = {}, None
+    extras, weak, modes = {}, None, {}
     if not args.no_extras and args.workload == "cfg2":
         if args.scaling == "strong" and world > 1:
             a2 = Arm("weak")
@@ -390,6 +390,20 @@ def main():
             del a3
             torch.cuda.empty_cache()
         select_workload(args.workload)
+        # opt-in modes on the headline workload (tolerance parity, never the default): tensor-core projection and MUFU exponentials
+        for name, env in (("projection_tc", {"MPCMMD_PROJ": "tc"}), ("fast_math", {"MPCMMD_MATH": "fast"})):
+            if args.projection == "tc" and name == "projection_tc":
+                continue
+            os.environ.update(env)
+            a4 = Arm(args.scaling)
+            ms4, _, r4, _ = a4.time_device(2, 3)
+            modes[name] = {"env": env, "value": a4.total_solves * 2 / (ms4 * 1e-3), "unit": "solves/s", "ms_per_step": ms4 / 2,
+                           "accepted": {c: int(r4[c][:, 1].sum().item()) for c in COSTS},
+                           "parity": "stage outputs within 1e-4 of the reference fixtures (tests); not bit-exact, not the default"}
+            for k in env:
+                os.environ.pop(k, None)
+            del a4
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -409,7 +423,7 @@ def main():
                             "parallelism": "episodes sharded %d-way, no data-path collective" % world, "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
                 "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat,
-                "other_workloads": extras, "weak_scaling": weak, "clocks": clk.summary()}
+                "other_workloads": extras, "opt_in_modes": modes, "weak_scaling": weak, "clocks": clk.summary()}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -45,7 +45,18 @@ __device__ __forceinline__ f2 exp2_nonpos(float xa, float xb) {
     const float sca = dm::u2f((dm::f2u(ta) << 23) + 0x3f800000u), scb = dm::u2f((dm::f2u(tb) << 23) + 0x3f800000u);
     return mul2(y, pack(sca, scb));
 }
+// MUFU.EX2 (opt-in fast-math mode only, MPCMMD_MATH=fast): 2^x to ~2^-22 relative, not reproducible on the CPU oracle
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 }  // namespace pk
+
+// Laplace kernel entries exp(-(d / sigma)) two at a time.  Exact contract (FM = false): sc2 = (1/sigma, 1/sigma), the product d * (1/sigma) is rounded, then the
+// contract's polynomial exp.  Fast-math (FM = true): sc2 = -(1/sigma) * log2(e) in both lanes and the exponentials run on the XU pipe (MUFU.EX2).
+template <bool FM>
+__device__ __forceinline__ pk::f2 lap2(float da, float db, pk::f2 sc2) {
+    const pk::f2 d = pk::mul2(pk::pack(da, db), sc2);
+    if constexpr (FM) { float a, b; pk::unpack(d, a, b); return pk::pack(pk::ex2_approx(a), pk::ex2_approx(b)); }
+    else return pk::exp2_nonpos(-pk::lo(d), -pk::hi(d));
+}
 
 #define ICF_THREADS 96
 #define ICF_MAX_S 128       // candidates per inner iteration handled by the one-warp selection (4 per lane)
@@ -107,12 +118,13 @@ __device__ __noinline__ int top_abs_exact(const float* __restrict__ row) {     /
 
 // the QP + MMD cost of one beta sample given its reduced set (indices ti, ascending |theta|) and bandwidth sigma
 // [compute_beta.py:70-91, 120-129]; bit-identical to the second half of beta_sample<NR> of k_risk.cuh
-template <int NR>
+template <int NR, bool FM = false>
 __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], float sigma, const float* __restrict__ D,
                                            float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
     constexpr int nm = NR * NR;
     const float rinv = 1.0f / sigma;
-    const pk::f2 rinv2 = pk::dup(rinv);
+    const float sc = FM ? -rinv * 1.44269504088896341f : rinv;
+    const pk::f2 rinv2 = pk::dup(sc);
     // ---- ker_mixed row sums: rowsum_i = sum_m exp(-(D[idx_i][m] * rinv)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]
     constexpr int NP = NR / 2;                       // pairs of reduced rows handled together
     pk::f2 rs2[NP > 0 ? NP : 1];
@@ -126,28 +138,19 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
     for (int m = 0; m + 1 < nm; m += 2) {
 #pragma unroll
         for (int p = 0; p < NP; p++) {
-            const pk::f2 d0 = pk::mul2(pk::pack(Dr[2 * p][m], Dr[2 * p + 1][m]), rinv2);
-            const pk::f2 d1 = pk::mul2(pk::pack(Dr[2 * p][m + 1], Dr[2 * p + 1][m + 1]), rinv2);
-            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d0), -pk::hi(d0)));
-            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d1), -pk::hi(d1)));
+            rs2[p] = pk::add2(rs2[p], lap2<FM>(Dr[2 * p][m], Dr[2 * p + 1][m], rinv2));
+            rs2[p] = pk::add2(rs2[p], lap2<FM>(Dr[2 * p][m + 1], Dr[2 * p + 1][m + 1], rinv2));
         }
         if constexpr (NR & 1) {
-            const pk::f2 dl = pk::mul2(pk::pack(Dr[NR - 1][m], Dr[NR - 1][m + 1]), rinv2);
-            const pk::f2 e = pk::exp2_nonpos(-pk::lo(dl), -pk::hi(dl));
+            const pk::f2 e = lap2<FM>(Dr[NR - 1][m], Dr[NR - 1][m + 1], rinv2);
             rsl = rsl + pk::lo(e); rsl = rsl + pk::hi(e);
         }
     }
     if constexpr (nm & 1) {                          // last column
         constexpr int m = nm - 1;
 #pragma unroll
-        for (int p = 0; p < NP; p++) {
-            const pk::f2 d0 = pk::mul2(pk::pack(Dr[2 * p][m], Dr[2 * p + 1][m]), rinv2);
-            rs2[p] = pk::add2(rs2[p], pk::exp2_nonpos(-pk::lo(d0), -pk::hi(d0)));
-        }
-        if constexpr (NR & 1) {
-            const float dl = Dr[NR - 1][m] * rinv;
-            rsl = rsl + pk::lo(pk::exp2_nonpos(-dl, -dl));
-        }
+        for (int p = 0; p < NP; p++) rs2[p] = pk::add2(rs2[p], lap2<FM>(Dr[2 * p][m], Dr[2 * p + 1][m], rinv2));
+        if constexpr (NR & 1) rsl = rsl + pk::lo(lap2<FM>(Dr[NR - 1][m], Dr[NR - 1][m], rinv2));
     }
     float rowsum[NR];
 #pragma unroll
@@ -163,12 +166,12 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
         for (int i = 0; i < NR; i++) {
             K[i][i] = 1.0f;
 #pragma unroll
-            for (int j = 0; j < i; j++) dv[e++] = -(Dr[i][ti[j]] * rinv);
+            for (int j = 0; j < i; j++) dv[e++] = Dr[i][ti[j]];
         }
         dv[NE] = dv[NE - 1];
         float ev[NE + 1];
 #pragma unroll
-        for (int q = 0; q < NE; q += 2) pk::unpack(pk::exp2_nonpos(dv[q], dv[q + 1]), ev[q], ev[q + 1]);
+        for (int q = 0; q < NE; q += 2) pk::unpack(lap2<FM>(dv[q], dv[q + 1], rinv2), ev[q], ev[q + 1]);
         e = 0;
 #pragma unroll
         for (int i = 0; i < NR; i++)
@@ -236,7 +239,7 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
 }
 
 // one beta sample of the inner CEM [compute_beta.py:113-129, 70-91]; bit-identical to beta_sample<NR> of k_risk.cuh
-template <int NR>
+template <int NR, bool FM = false>
 __device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
                                                   float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
     constexpr int nm = NR * NR;
@@ -263,7 +266,7 @@ __device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __
 #pragma unroll
         for (int p = 0; p < NR; p++) ti[p] = (pkd >> (5 * p)) & 31;
     }
-    return beta_eval<NR>(c, ti, row[nm], D, beta_out, idx_out);
+    return beta_eval<NR, FM>(c, ti, row[nm], D, beta_out, idx_out);
 }
 
 // float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order of the costs)
@@ -501,7 +504,8 @@ __device__ __forceinline__ void icf_mvn_row_regs(const float* __restrict__ LT, i
 
 // LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): no register cap (156 instead of the 56 registers
 // that let 12 chains share an SM) and the resampling normals prefetched behind the Cholesky (mmd_opt p50 at batch 1: 8.3 -> 7.4 ms)
-template <int NR, bool LAT>
+// FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
+template <int NR, bool LAT, bool FM = false>
 __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;      // where this iteration's new rows live
         // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
 #pragma unroll 1
-        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
+        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR, FM>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
         if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);

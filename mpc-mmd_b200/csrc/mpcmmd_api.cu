@@ -61,6 +61,7 @@ struct mpcmmd_handle_s {
     int sm_count = 148;
     int inner_mode = 0;        // 0 auto, 1 warp-per-chain, 2 CTA-per-chain, 3 generic, 4 CTA-per-chain latency build, 5 phase-split (MPCMMD_INNER_CEM=auto|warp|cta|generic|lat|split)
     int E = 0;
+    bool fast_math = false;    // MPCMMD_MATH=fast: Laplace-kernel exponentials of the inner CEM on MUFU.EX2 (opt-in, tolerance parity only)
     bool proj_tc = false;      // MPCMMD_PROJ=tc: tensor-core projection kernel (k_project_tc)
     bool proj_tc_always = false;
     std::vector<void*> allocs;
@@ -133,7 +134,7 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6 };
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7 };
 #define INNER_DEFAULT_THROUGHPUT INNER_CTA
 typedef void (*pipe_fn)(DCfg, RollArgs, float*);
 // the pipelined kernel stages the mother features through its row buffer: (S - ne) rows of nm + 1 (odd stride) must hold nm x 22 floats
@@ -164,6 +165,9 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_CTA) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, false>; case 3: return k_inner_cem_fast<3, false>; case 4: return k_inner_cem_fast<4, false>; case 5: return k_inner_cem_fast<5, false>;
     }
+    if (kind == INNER_CTA_FASTMATH) switch (d.nr) {
+        case 2: return k_inner_cem_fast<2, false, true>; case 3: return k_inner_cem_fast<3, false, true>; case 4: return k_inner_cem_fast<4, false, true>; case 5: return k_inner_cem_fast<5, false, true>;
+    }
     if (kind == INNER_CTA_LAT) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, true>; case 3: return k_inner_cem_fast<3, true>; case 4: return k_inner_cem_fast<4, true>; case 5: return k_inner_cem_fast<5, true>;
     }
@@ -182,7 +186,7 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
 }
 static size_t inner_cem_smem_kind(const DCfg& d, int kind) {
     if (kind == INNER_WARP) return (size_t)warp_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
-    if (kind == INNER_CTA || kind == INNER_CTA_LAT) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
     return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
 }
 
@@ -347,7 +351,9 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
             if (mb) h->pipe_minb = atoi(mb);
             if (raise_smem(device, (const void*)pipe_kernel(d.nr, h->pipe_minb), pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), true)) return fail("k_inner_cem_pipe smem opt-in failed");
         }
-        for (int kind = INNER_WARP; kind <= INNER_CTA_LAT; kind++) {
+        { const char* mm = getenv("MPCMMD_MATH"); h->fast_math = mm && !strcmp(mm, "fast"); }
+        for (int kind = INNER_WARP; kind <= INNER_CTA_FASTMATH; kind++) {
+            if (kind == INNER_SPLIT || kind == INNER_PIPE) continue;
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
             inner_cem_fn f = inner_cem_kernel(d, kind);
             if (!f) continue;
@@ -434,6 +440,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         // a launch of at most 3 chains per SM (one episode = 100 chains) is pure dependency latency: the latency build of the fused kernel
         if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 3 * h->sm_count ? INNER_CTA_LAT : INNER_DEFAULT_THROUGHPUT);
         if (kind == INNER_PIPE && !pipe_ok(d)) kind = INNER_CTA;
+        if (kind == INNER_CTA && h->fast_math) kind = INNER_CTA_FASTMATH;
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
         if (kind != INNER_SPLIT && kind != INNER_PIPE) {
             f = inner_cem_kernel(d, kind);
@@ -441,7 +448,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         }
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
-        if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
+        if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_CTA_FASTMATH && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
             if (!h->rolls_x) return fail("internal: mother-rollout scratch not allocated");
             ra.write_rolls = 1; ra.xroll = h->rolls_x; ra.yroll = h->rolls_y;
         }
@@ -474,9 +481,9 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     } else if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
         if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
-        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
+        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
-        if (kind == INNER_CTA || kind == INNER_CTA_LAT) {
+        if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) {
             { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
             if (n_launch) *n_launch = 3;
         }

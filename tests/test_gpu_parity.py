@@ -174,14 +174,19 @@ def test_stage_project_tensor_core_ragged_tiles(mods, monkeypatch, n):
 
 
 def test_solve_with_tensor_core_projection(mods, monkeypatch):
-    """Full cvar / mmd_opt solves with MPCMMD_PROJ=tc: finite, boundary coefficients pinned, and the planned speed profile close to the
-    exact path's.  Trajectories are NOT compared tightly: the reference's first elite stage ranks projection residuals that are pure
-    round-off for feasible samples (cem.py:233), so any two float32 implementations keep different rows."""
+    """MPCMMD_PROJ=tc over the whole 200-episode sweep of configs[1] (cvar + mmd_opt), against the exact projection on the same episodes.
+
+    What can and cannot be compared: the reference's first elite stage keeps the 20 smallest projection residuals (cem.py:233), and for feasible
+    samples those residuals are pure float32 round-off (~5e-6), so ANY change of rounding -- XLA vs NumPy vs this tf32-split kernel -- keeps other
+    rows and the CEM iterates of one episode diverge.  Per-episode trajectories are therefore not comparable beyond the
+    boundary conditions; what a user of the sweep consumes is comparable: WHICH episodes are accepted (main_mpc.py:121-128) and the distribution
+    of the planned motion.  This test pins, at sweep level: boundary coefficients to 1e-5, accepted sets (Jaccard >= 0.9, counts within 4 %),
+    and the 10 / 50 / 90 % quantiles of the distance covered and of the final lateral position."""
     cem_impl, O = mods
     args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
     ora = O.OracleCEM(*args, variant="static")
     init_state, mean, cov, v_des = O.driver_inputs("static")
-    E = 4
+    E = 200
     idx, xo, yo = _episodes(O, ora, E, 4)
     res = {}
     for tag in ("exact", "tc"):
@@ -192,13 +197,26 @@ def test_solve_with_tensor_core_projection(mods, monkeypatch):
         prob = cem_impl.CEM(*args, variant="static", max_episodes=E)
         res[tag] = {c: prob.solve_batch(c, idx, np.stack([init_state] * E), np.stack([mean] * E), np.stack([cov] * E), xo, yo, [v_des] * E)
                     for c in ("cvar", "mmd_opt")}
-    for c in ("cvar", "mmd_opt"):
+        del prob
+    P_end = np.ones(11); P_end[:-1] = 0.0                                    # Bernstein basis at t_fin: the last coefficient is the end point
+    for c, thr in (("cvar", 1e-5), ("mmd_opt", -999.0)):                    # main_mpc.py:88-97
         t, x = res["tc"][c], res["exact"][c]
         for k in ("cx", "cy", "cost_obs", "cost_lane"):
             assert np.isfinite(t[k]).all(), (c, k)
         np.testing.assert_allclose(t["cx"][:, :3], x["cx"][:, :3], rtol=1e-5, atol=1e-5)      # x0, v0, a0 boundary conditions
         np.testing.assert_allclose(t["cy"][:, :3], x["cy"][:, :3], rtol=1e-5, atol=1e-5)
-        assert np.abs(t["cx"][:, -1] - x["cx"][:, -1]).max() <= 0.25 * np.abs(x["cx"][:, -1]).max()    # distance covered over the horizon
+        at, ax = t["cost_obs"] <= thr, x["cost_obs"] <= thr
+        jac = (at & ax).sum() / max((at | ax).sum(), 1)
+        print(f"{c}: accepted exact {ax.sum()} tc {at.sum()} Jaccard {jac:.3f}")
+        assert jac >= 0.9 and abs(int(at.sum()) - int(ax.sum())) <= 0.04 * E, (c, jac, at.sum(), ax.sum())
+        qt, qx = np.quantile(t["cx"][:, -1], [0.1, 0.5, 0.9]), np.quantile(x["cx"][:, -1], [0.1, 0.5, 0.9])
+        print(f"{c}: distance covered quantiles exact {qx} tc {qt}")
+        assert np.abs(qt - qx).max() <= 0.03 * np.abs(x["cx"][:, -1]).max(), (c, qt, qx)
+        # the final lateral position is bimodal (the plan ends in the left or in the right lane), so compare the split and the spread, not the median
+        lt, lx = float((t["cy"][:, -1] > 0).mean()), float((x["cy"][:, -1] > 0).mean())
+        qt, qx = np.quantile(np.abs(t["cy"][:, -1]), [0.1, 0.5, 0.9]), np.quantile(np.abs(x["cy"][:, -1]), [0.1, 0.5, 0.9])
+        print(f"{c}: ends left of the centre line exact {lx:.3f} tc {lt:.3f}; |y_end| quantiles exact {qx} tc {qt}")
+        assert abs(lt - lx) <= 0.08 and np.abs(qt - qx).max() <= 0.25, (c, lt, lx, qt, qx)
 
 
 def test_stage_noise_bit_exact(mods):
@@ -337,6 +355,35 @@ def test_inner_cem_kernel_variants_bit_exact(mods, monkeypatch, mode, nr, npr, n
         ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
         for k in ("risk", "lane", "beta", "sigma", "res_beta"):
             _eq(got[k][i], ref[k], f"{mode} nr={nr} chain {i} {k}")
+
+
+@pytest.mark.parametrize("mode", ["cta", "pipe", "split"])
+def test_inner_cem_repeatable_under_load(mods, monkeypatch, mode):
+    """Race detector of last resort (compute-sanitizer is closed on this GPU pool, profiles/r02_sanitizer.md): the kernels that alias live
+    shared-memory regions across barriers (k_inner_cem_fast), hand-roll a named-barrier producer/consumer protocol (k_inner_cem_pipe) or pass
+    chain state through L2 between launches (k_icem_*) run a launch of several waves of CTAs four times; every output bit must repeat, and
+    sampled chains must equal the oracle.  A data race or a missing fence shows up as run-to-run or chain-to-chain differences."""
+    monkeypatch.setenv("MPCMMD_INNER_CEM", mode)
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=5)
+    prob, ora = _pair(mods, (5, 2, 0.1, 20, "gaussian", 0.0, 0.0), max_episodes=60, **kw)
+    rng = np.random.default_rng(41)
+    base_acc, base_steer = _controls(ora, rng, 12)
+    n = 5003                                                   # odd: the two-chain CTAs of the pipelined kernel end on a single chain
+    pick = rng.integers(0, 12, n)
+    acc = (base_acc[pick] * rng.uniform(0.5, 1.5, (n, 1))).astype(f32); steer = (base_steer[pick] * rng.uniform(0.5, 1.5, (n, 1))).astype(f32)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(57, 3)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(2, 1)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    first = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+    for rep in range(3):
+        again = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(again[k], first[k], f"{mode} repeat {rep} {k}")
+    for i in list(range(0, n, 211)) + [n - 1]:
+        ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(first[k][i], ref[k], f"{mode} chain {i} {k}")
 
 
 def test_inner_cem_warp_persistent_grid_strides_over_chains(mods, monkeypatch):
