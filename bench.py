@@ -20,6 +20,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -243,36 +244,57 @@ def main():
         def __init__(self, scaling):
             self.eps = shard(EPISODES, rank, world, scaling)
             self.E = len(self.eps)
-            self.prob = CEM(*cem_args(), variant=VARIANT, max_episodes=max(self.E, 1), device=local, **CEM_KW)
+            # one handle and one CUDA stream per cost function: the solves of the sweep's cost functions are independent and run concurrently
+            # (the reference's main_mpc.py loops over them serially, main_mpc.py:84-104)
+            self.probs = {c: CEM(*cem_args(), variant=VARIANT, max_episodes=max(self.E, 1), device=local, **CEM_KW) for c in COSTS}
+            self.prob = self.probs[COSTS[-1]]
+            self.streams = {c: torch.cuda.Stream(dev) for c in COSTS}
+            self.pool = ThreadPoolExecutor(max_workers=len(COSTS))
             self.host = scenes.static_batch(self.prob, self.eps, VARIANT)
             self.dev_in = {k: torch.as_tensor(self.host[k], device=dev) for k in keys}
             self.pinned_np = {k: torch.as_tensor(self.host[k]).pin_memory().numpy() for k in keys}
             self.thresholds = {c: (-self.prob.ker_wt + 1.0 if c in ("mmd_opt", "mmd_random") else 1e-5) for c in COSTS}     # main_mpc.py:88-97
+            self.k_col = torch.as_tensor(self.eps, device=dev, dtype=torch.float32)[:, None]
             self.total_solves = EPISODES * len(COSTS) * (1 if scaling == "strong" else world)
 
-        def record(self, out, cost):
-            """26-float per-episode record [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] gathered over ranks; shards are
-            ragged under strong scaling (200 = 8 x 25 is even, 3- or 7-way is not), so every rank pads to the largest shard"""
-            rec = torch.cat([torch.as_tensor(self.eps, device=dev, dtype=torch.float32)[:, None], (out["cost_obs"] <= self.thresholds[cost]).float()[:, None],
-                             out["cost_obs"][:, None], out["cost_lane"][:, None], out["cx"], out["cy"]], 1)
+        def record(self, outs):
+            """26-float per-episode records [k, accepted, cost_obs, cost_lane, cx(11), cy(11)] of every cost function, gathered over the ranks in ONE
+            NCCL all_gather.  Shards are ragged under strong scaling (200 = 8 x 25 is even, 3- or 7-way is not): every rank pads to the
+            largest shard with k = -1 rows, which `unpad` drops after the timed region (boolean indexing would synchronise the host inside it)."""
+            recs = []
+            for cost in COSTS:
+                out = outs[cost]
+                recs.append(torch.cat([self.k_col, (out["cost_obs"] <= self.thresholds[cost]).float()[:, None], out["cost_obs"][:, None],
+                                       out["cost_lane"][:, None], out["cx"], out["cy"]], 1))
+            rec = torch.stack(recs, 0)                                  # (costs, E, 26)
             if world > 1:
                 m = (EPISODES + world - 1) // world if len(self.eps) != EPISODES else EPISODES
-                pad = torch.full((m, 26), -1.0, device=dev); pad[:rec.shape[0]] = rec
-                buf = [torch.empty_like(pad) for _ in range(world)]
-                dist.all_gather(buf, pad)
-                rec = torch.cat(buf, 0)
-                rec = rec[rec[:, 0] >= 0]
+                pad = torch.full((len(COSTS), m, 26), -1.0, device=dev); pad[:, :rec.shape[1]] = rec
+                buf = torch.empty((world,) + tuple(pad.shape), device=dev)
+                dist.all_gather_into_tensor(buf, pad)
+                rec = buf.permute(1, 0, 2, 3).reshape(len(COSTS), world * m, 26)
             return rec
 
+        @staticmethod
+        def unpad(rec):
+            return {cost: rec[i][rec[i][:, 0] >= 0] for i, cost in enumerate(COSTS)}
+
         def step_device(self):
-            recs = {}
+            cur = torch.cuda.current_stream(dev)
+            outs = {}
             for cost in COSTS:
-                out = self.prob.solve_batch_device(cost, *[self.dev_in[k] for k in keys])
-                recs[cost] = self.record(out, cost)
-            return recs
+                st = self.streams[cost]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    outs[cost] = self.probs[cost].solve_batch_device(cost, *[self.dev_in[k] for k in keys])
+            for cost in COSTS:
+                cur.wait_stream(self.streams[cost])
+            return self.record(outs)
 
         def step_host(self):
-            return {cost: self.prob.solve_batch(cost, *[self.pinned_np[k] for k in keys]) for cost in COSTS}
+            """host buffers in, host buffers out: one synchronous C-ABI call per cost function, issued from one host thread each"""
+            futs = {cost: self.pool.submit(self.probs[cost].solve_batch, cost, *[self.pinned_np[k] for k in keys]) for cost in COSTS}
+            return {cost: f.result() for cost, f in futs.items()}
 
         def time_device(self, K, W, clocks=None):
             """K timed steps, device-resident inputs, CUDA events per step, L2 flushed between steps; returns (ms_total max over ranks, wall, recs, launches/step)"""
@@ -280,7 +302,7 @@ def main():
                 self.step_device()
             launches = 0
             for cost in COSTS:            # graphs are cached now; count launches per solve batch
-                self.prob.solve_batch_device(cost, *[self.dev_in[k] for k in keys]); launches += self.prob.last_launch_count()
+                self.probs[cost].solve_batch_device(cost, *[self.dev_in[k] for k in keys]); launches += self.probs[cost].last_launch_count()
             barrier()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
             barrier()
@@ -292,7 +314,7 @@ def main():
                 ev[i][1].record()
             barrier()
             wall = time.perf_counter() - t0
-            return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)), wall, recs, launches
+            return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)), wall, self.unpad(recs), launches
 
     # ---- device-resident throughput (`value`) on the headline workload
     arm = Arm(args.scaling)
@@ -322,8 +344,8 @@ def main():
     prof = prob.profile_solve(HEAVY, E)
     prof_cvar = None
     if "cvar" in COSTS and HEAVY != "cvar":
-        prob.solve_batch_device("cvar", *[arm.dev_in[k] for k in keys]); torch.cuda.synchronize()
-        prof_cvar = prob.profile_solve("cvar", E)
+        arm.probs["cvar"].solve_batch_device("cvar", *[arm.dev_in[k] for k in keys]); torch.cuda.synchronize()
+        prof_cvar = arm.probs["cvar"].profile_solve("cvar", E)
     fl = scenes.flops_per_sample(HEAVY, WORK["num_reduced"], WORK["num_prime"], WORK["num_obs"])
     flops_per_launch = fl["risk"] * prob.num_batch * E
     avg_launch_s = prof["ms"]["risk"] * 1e-3 / prof["launches"]["risk"]
@@ -419,7 +441,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": line_config(args.scaling),
-                "details": {"episodes_this_rank": E, "projection": args.projection, "l2": "flushed between timed steps (256 MiB fill)",
+                "details": {"episodes_this_rank": E, "projection": args.projection, "concurrency": "one handle + CUDA stream per cost function (cvar and mmd_opt solve concurrently)", "l2": "flushed between timed steps (256 MiB fill)",
                             "parallelism": "episodes sharded %d-way, no data-path collective" % world, "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
                 "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat,

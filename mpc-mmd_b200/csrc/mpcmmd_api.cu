@@ -69,7 +69,38 @@ struct mpcmmd_handle_s {
     std::map<std::pair<int, int>, int> graph_launches;
     int last_launches = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;       // second branch of a solve graph whose episodes are split into two groups (see solve_groups)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int groups_override = 0;                 // MPCMMD_GROUPS=1|2: force the number of episode groups of a solve graph (0 = automatic)
 };
+
+// ---- episode-offset view of a handle's workspace: every per-episode array advanced by e0 episodes.  A solve graph can then enqueue disjoint episode
+// ranges on different streams with the unchanged launch code (episodes are independent; sample index g and episode index e stay relative to the view).
+struct ViewSave { DWork w; float *beq_x, *beq_y, *state0, *feat, *ctrl, *bscratch, *throws, *split_state, *rolls_x, *rolls_y, *xroll; int* ridx; };
+static ViewSave push_view(mpcmmd_handle_s* h, int e0) {
+    ViewSave sv = {h->w, h->beq_x, h->beq_y, h->state0, h->feat, h->ctrl, h->bscratch, h->throws, h->split_state, h->rolls_x, h->rolls_y, h->xroll, h->ridx};
+    if (e0 == 0) return sv;
+    const DCfg& d = h->d; DWork& w = h->w;
+    const size_t e = (size_t)e0, B = d.B, n = (size_t)d.nr * d.np, ncem = (size_t)(d.B - d.n_el) * NPAR, it = d.iters;
+#define ADV(p, stride) if (p) p += e * (stride)
+    ADV(w.params, B * NPAR); ADV(w.lam_x, B * NV); ADV(w.lam_y, B * NV); ADV(w.s_lane, B * 2 * NL); ADV(w.mean, NPAR); ADV(w.cov, 64);
+    ADV(w.cx, B * NV); ADV(w.cy, B * NV); ADV(w.res_norm, B); ADV(w.cost_base, B); ADV(w.acc, B * T_); ADV(w.steer, B * T_); ADV(w.risk, B); ADV(w.lane, B);
+    ADV(w.beta, B * d.nr); ADV(w.sigma, B); ADV(w.res_beta, B * d.iters_in); ADV(w.z1, it * n); ADV(w.z2, it * n); ADV(w.z3, it * n); ADV(w.zcem, it * ncem);
+    ADV(w.keys, it * 4); ADV(w.btab, it * 4 * GT_FIELDS * n); ADV(w.idx_mpc, 1); ADV(w.init_state, 6); ADV(w.mean0, NPAR); ADV(w.cov0, 64);
+    ADV(w.x_obs, (size_t)d.O * T_); ADV(w.y_obs, (size_t)d.O * T_); ADV(w.v_des, 1);
+    ADV(w.o_cx, NV); ADV(w.o_cy, NV); ADV(w.o_lane, 1); ADV(w.o_obs, 1); ADV(w.o_beta, d.nr); ADV(w.o_sigma, 1); ADV(w.o_res_beta, d.iters_in); ADV(w.o_sel, it);
+    ADV(h->beq_x, 3); ADV(h->beq_y, 4); ADV(h->state0, 5);
+    ADV(h->feat, B * d.nm * 2 * NV); ADV(h->ctrl, B * 2 * n); ADV(h->ridx, B * d.nr); ADV(h->bscratch, B * d.S_in * (d.nr + 1));
+    ADV(h->throws, B * (d.nm + 1) * ICP_TH_LD); ADV(h->split_state, B * (size_t)split_layout(d.nr, d.S_in, d.n_el_in).total);
+    ADV(h->rolls_x, B * d.nm * d.np); ADV(h->rolls_y, B * d.nm * d.np);
+    if (h->xroll) h->xroll = h->feat;
+#undef ADV
+    return sv;
+}
+static void pop_view(mpcmmd_handle_s* h, const ViewSave& sv) {
+    h->w = sv.w; h->beq_x = sv.beq_x; h->beq_y = sv.beq_y; h->state0 = sv.state0; h->feat = sv.feat; h->ctrl = sv.ctrl; h->bscratch = sv.bscratch;
+    h->throws = sv.throws; h->split_state = sv.split_state; h->rolls_x = sv.rolls_x; h->rolls_y = sv.rolls_y; h->xroll = sv.xroll; h->ridx = sv.ridx;
+}
 
 template <typename Tp>
 static int dalloc(mpcmmd_handle_s* h, Tp** p, size_t n) {
@@ -368,6 +399,9 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
         }
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    { const char* gv = getenv("MPCMMD_GROUPS"); h->groups_override = gv ? atoi(gv) : 0; }
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     return 0;
@@ -379,6 +413,9 @@ extern "C" int mpcmmd_destroy(mpcmmd_handle h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (void* p : h->allocs) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return 0;
 }
@@ -526,6 +563,14 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
     return 0;
 }
 
+// number of episode groups of a solve graph.  Two groups pay off for mmd_opt launches of a few waves of chains (strong-scaled shards: 25 episodes = 2500
+// chains on 1776 resident CTAs): measured 27.8 -> 25.2 ms per cvar + mmd_opt step at 25 episodes, neutral from ~100 episodes on (tools/stream_probe.py)
+static int solve_groups(const mpcmmd_handle_s* h, int kind, int n_ep) {
+    if (n_ep < 2 || h->inner_mode == INNER_WARP) return 1;         // the warp-per-chain kernel's row stash is per persistent CTA, not per chain
+    if (h->groups_override == 1 || h->groups_override == 2) return h->groups_override;
+    const long long chains = (long long)n_ep * h->d.B;
+    return (kind == MPCMMD_COST_MMD_OPT && inner_cem_is_fast(h->d) && chains > 6LL * h->sm_count && chains <= 36LL * h->sm_count) ? 2 : 1;
+}
 static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
     auto key = std::make_pair(kind, n_ep);
     auto it = h->graphs.find(key);
@@ -533,7 +578,20 @@ static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* ou
     cudaGraph_t g;
     int launches = 0;
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_solve(h, kind, n_ep, h->own_stream, &launches);
+    int rc = 0;
+    if (solve_groups(h, kind, n_ep) == 2) {
+        // two episode groups on two branches of the graph: the small latency-bound kernels of one group (projection, rollouts, selection) overlap
+        // the reduced-set kernel of the other, and the tail wave of one group's chains is filled by the other group's
+        const int nA = (n_ep + 1) / 2, nB = n_ep - nA;
+        int la = 0, lb = 0;
+        cudaEventRecord(h->ev_fork, h->own_stream);
+        cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0);
+        rc = enqueue_solve(h, kind, nA, h->own_stream, &la);
+        if (!rc) { const ViewSave sv = push_view(h, nA); rc = enqueue_solve(h, kind, nB, h->aux_stream, &lb); pop_view(h, sv); }
+        cudaEventRecord(h->ev_join, h->aux_stream);
+        cudaStreamWaitEvent(h->own_stream, h->ev_join, 0);
+        launches = la + lb;
+    } else rc = enqueue_solve(h, kind, n_ep, h->own_stream, &launches);
     cudaError_t ce = cudaStreamEndCapture(h->own_stream, &g);
     if (rc) { if (ce == cudaSuccess && g) cudaGraphDestroy(g); return -1; }
     CK(ce);
