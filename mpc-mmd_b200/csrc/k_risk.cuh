@@ -112,25 +112,41 @@ __device__ __forceinline__ float mmd_cost_warp(const DCfg& c, const float* beta,
     }
     return c.ker_wt * (s1 - 2.0f * s2);
 }
-// jnp.quantile (linear interpolation) + mean of the tail  [costs.py:213-220]
-__device__ __noinline__ float cvar_cost(const DCfg& c, const float* v) {
+// CVaR of nr per-rollout costs: jnp.quantile (linear interpolation) + mean of the tail  [costs.py:213-220], by a whole warp (num_reduced <= 64): the two
+// order statistics the quantile needs come from a stable RANK COUNT -- lane l ranks
+// elements l and l + 32 against all nr values (O(nr) per lane instead of lane 0's O(nr^2) insertion sort), the lanes holding ranks floor(q) / ceil(q)
+// broadcast their values -- and the tail mean keeps the contract's sequential ascending-index sum (nr adds on one lane): the value of a stable sort + scan, bit for bit.
+__device__ __forceinline__ float cvar_cost_warp(const DCfg& c, const float* v, int lane) {
     const int nr = c.nr;
-    int perm[MPCMMD_MAX_NR_DEV];
-    for (int i = 0; i < nr; i++) {            // stable insertion sort, NaN last
-        int j = i;
-        while (j > 0 && dm::lt_nanlast(v[i], v[perm[j - 1]])) { perm[j] = perm[j - 1]; j--; }
-        perm[j] = i;
-    }
-    float q = c.alpha_quant * (float)(nr - 1);
-    float lo = floorf(q), hi = ceilf(q);
-    float hw = q - lo, lw = 1.0f - hw;
+    const float q = c.alpha_quant * (float)(nr - 1);
+    const float lo = floorf(q), hi = ceilf(q);
+    const float hw = q - lo, lw = 1.0f - hw;
     int ilo = (int)lo, ihi = (int)hi;
     ilo = ilo < 0 ? 0 : (ilo > nr - 1 ? nr - 1 : ilo);
     ihi = ihi < 0 ? 0 : (ihi > nr - 1 ? nr - 1 : ihi);
-    float var = v[perm[ilo]] * lw + v[perm[ihi]] * hw;
+    float vlo = 0.0f, vhi = 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        const float vi = i < nr ? v[i] : 0.0f;
+        int rank = -1;
+        if (i < nr) {
+            rank = 0;
+            for (int j = 0; j < nr; j++) {
+                const float vj = v[j];
+                const bool less = dm::lt_nanlast(vj, vi), tie = !less && !dm::lt_nanlast(vi, vj);
+                rank += (less || (tie && j < i)) ? 1 : 0;             // stable ascending order, NaN last
+            }
+        }
+        const unsigned mlo = __ballot_sync(FULL, rank == ilo), mhi = __ballot_sync(FULL, rank == ihi);
+        const float slo = __shfl_sync(FULL, vi, mlo ? __ffs(mlo) - 1 : 0), shi = __shfl_sync(FULL, vi, mhi ? __ffs(mhi) - 1 : 0);
+        if (mlo) vlo = slo;
+        if (mhi) vhi = shi;
+    }
+    const float var = vlo * lw + vhi * hw;
     float s = 0.0f; int n = 0;
-    for (int i = 0; i < nr; i++) if (v[i] >= var) { s = s + v[i]; n++; }
-    return n > 0 ? s / (float)n : 0.0f;
+    if (lane == 0) for (int i = 0; i < nr; i++) if (v[i] >= var) { s = s + v[i]; n++; }
+    return n > 0 ? s / (float)n : 0.0f;          // valid on lane 0
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,12 +331,13 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             __syncwarp();
             const float risk = mmd_cost_warp(c, bet, cst, c.sigma_random, lane);
             if (lane == 0) { a.sigma[g] = c.sigma_random; a.risk[g] = risk; a.lane[g] = 0.0f; }
+        } else if (a.cost_kind == 2) {                    // cvar  [costs.py:206-221, 137-158]: warp-level rank selection of the two quantile order statistics
+            const float risk = cvar_cost_warp(c, cst, lane);
+            const float lanec = cvar_cost_warp(c, lb, lane) + cvar_cost_warp(c, ub, lane);
+            if (lane == 0) { a.risk[g] = risk; a.lane[g] = lanec; }
         } else if (lane == 0) {
             float risk, lanec;
-            if (a.cost_kind == 2) {                       // cvar  [costs.py:206-221, 137-158]
-                risk = cvar_cost(c, cst);
-                lanec = cvar_cost(c, lb) + cvar_cost(c, ub);
-            } else {                                      // saa  [costs.py:223-234, 160-171]
+            {                                             // saa  [costs.py:223-234, 160-171]
                 float s = 0.0f, sl = 0.0f, su = 0.0f;
                 for (int i = 0; i < nr; i++) { s = s + (cst[i] > 0.0f ? 1.0f : 0.0f); sl = sl + (lb[i] > 0.0f ? 1.0f : 0.0f); su = su + (ub[i] > 0.0f ? 1.0f : 0.0f); }
                 risk = s / (float)nr;

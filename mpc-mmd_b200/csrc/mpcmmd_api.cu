@@ -17,6 +17,7 @@
 #include "k_inner_cem_warp.cuh"
 #include "k_inner_split.cuh"
 #include "k_inner_pipe.cuh"
+#include "k_inner_big.cuh"
 #include "k_select.cuh"
 #include "k_validate.cuh"
 
@@ -55,6 +56,8 @@ struct mpcmmd_handle_s {
     float* ctrl = nullptr;     // [E*B][2][nr*np] noisy controls (k_rollouts -> k_opt_risk)
     float* throws = nullptr;        // [E*B][nm+1][ICP_TH_LD] candidate-elite rows of the pipelined inner CEM (k_inner_pipe.cuh)
     int pipe_minb = 8;              // CTAs per SM the pipelined kernel is compiled for (MPCMMD_PIPE_MINB=8|9|12)
+    float* big_state = nullptr;     // [big_chunk][BigLayout::total] chain blocks of k_inner_cem_big (num_reduced > 10), reused by successive chain ranges
+    int big_chunk = 0;
     float* split_state = nullptr;   // [E*B][SplitLayout::total] chain blocks of the phase-split inner CEM (k_inner_split.cuh)
     float* stash = nullptr;    // row stash of k_inner_cem_warp, [warp_grid][S][32]
     int warp_grid = 0;         // persistent CTAs of k_inner_cem_warp (SMs x resident CTAs per SM)
@@ -165,7 +168,8 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7 };
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7, INNER_BIG = 8 };
+#define MPCMMD_BIG_SCRATCH_BYTES ((size_t)8 << 30)      // global chain state of k_inner_cem_big held at a time (num_reduced 40: 23 MB per chain)
 #define INNER_DEFAULT_THROUGHPUT INNER_CTA
 typedef void (*pipe_fn)(DCfg, RollArgs, float*);
 // the pipelined kernel stages the mother features through its row buffer: (S - ne) rows of nm + 1 (odd stride) must hold nm x 22 floats
@@ -232,7 +236,7 @@ extern "C" int mpcmmd_create(const mpcmmd_config* cfg, int device, mpcmmd_handle
     if (B < cfg->ellite_num_cost || cfg->ellite_num_cost > 32 || cfg->ellite_num > 8 || cfg->ellite_num > cfg->ellite_num_cost)
         return fail("mpcmmd_create: need ellite_num <= 8, ellite_num <= ellite_num_cost <= min(32, num_batch)");
     if (np < 2 || np > MPCMMD_T) return fail("mpcmmd_create: num_prime must be in [2,100]");
-    if (nr < 2 || nr > MPCMMD_MAX_NR_DEV) return fail("mpcmmd_create: num_reduced must be in [2,64] (mmd_opt: 2..10)");
+    if (nr < 2 || nr > MPCMMD_MAX_NR_DEV) return fail("mpcmmd_create: num_reduced must be in [2,64] (mmd_opt: 2..40)");
     if (cfg->num_obs < 1 || E < 1) return fail("mpcmmd_create: num_obs and max_episodes must be >= 1");
     if (cfg->num_samples_cem > RISKO_THREADS * 8 || cfg->num_ellite_beta < 2 || cfg->num_ellite_beta >= cfg->num_samples_cem)
         return fail("mpcmmd_create: bad inner-CEM sizes");
@@ -363,7 +367,7 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
     if (raise_smem(device, (const void*)k_project, PROJ_SMEM_BYTES)) return fail("k_project smem opt-in failed");
     if (raise_smem(device, (const void*)k_project_tc, ptc::SMEM_BYTES, true)) return fail("k_project_tc smem opt-in failed");
     {
-        size_t rs = nr <= MPCMMD_MAX_NR ? roll_smem(h, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(h, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
+        size_t rs = nr <= MPCMMD_MAX_NR_OPT ? roll_smem(h, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(h, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory");
         if (raise_smem(device, (const void*)k_rollouts<ROLL_OPT>, rs) || raise_smem(device, (const void*)k_rollouts<ROLL_FLY>, rs) ||
             raise_smem(device, (const void*)k_rollouts<ROLL_STAGED>, rs)) return fail("k_rollouts smem opt-in failed");
@@ -444,8 +448,14 @@ static int launch_project(mpcmmd_handle_s* h, const ProjArgs& p, cudaStream_t s)
 // mother rollouts / features scratch of the mmd_opt path, allocated on first use ([E*B][nm][np] x2 and [E*B][nm][22])
 static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     if (h->xroll) return 0;
-    if (!inner_cem_kernel(h->d, INNER_GENERIC)) return fail("mmd_opt: num_reduced must be 2..10 (larger reduced sets: cvar / saa / mmd_random only)");
+    if (h->d.nr > MPCMMD_MAX_NR_OPT) return fail("mmd_opt: num_reduced must be in [2, 40] (larger reduced sets: cvar / saa / mmd_random only)");
     const DCfg& d = h->d; const size_t EB = (size_t)h->E * d.B;
+    if (d.nr > MPCMMD_MAX_NR) {      // large reduced sets: chain state in global memory, as many chains at a time as the scratch budget holds
+        const size_t per = big_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+        size_t chunk = MPCMMD_BIG_SCRATCH_BYTES / per; if (chunk < 1) chunk = 1; if (chunk > EB) chunk = EB;
+        h->big_chunk = (int)chunk;
+        if (dalloc(h, &h->big_state, chunk * (per / sizeof(float)))) return -1;
+    }
     if (dalloc(h, &h->feat, EB * d.nm * 2 * NV) || dalloc(h, &h->ctrl, EB * 2 * d.nr * d.np)) return -1;
     // the mother rollouts are stored only for the kernels that read them back (generic / warp-per-chain); allocated on first such launch
     h->xroll = h->feat;     // non-null marker: scratch is ready
@@ -476,10 +486,11 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the build with the 96-register budget
         // a launch of at most 3 chains per SM (one episode = 100 chains) is pure dependency latency: the latency build of the fused kernel
         if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 3 * h->sm_count ? INNER_CTA_LAT : INNER_DEFAULT_THROUGHPUT);
+        if (d.nr > MPCMMD_MAX_NR) kind = INNER_BIG;
         if (kind == INNER_PIPE && !pipe_ok(d)) kind = INNER_CTA;
         if (kind == INNER_CTA && h->fast_math) kind = INNER_CTA_FASTMATH;
         if (kind == INNER_WARP && !h->stash) return fail("internal: row stash of k_inner_cem_warp not allocated");
-        if (kind != INNER_SPLIT && kind != INNER_PIPE) {
+        if (kind != INNER_SPLIT && kind != INNER_PIPE && kind != INNER_BIG) {
             f = inner_cem_kernel(d, kind);
             if (!f) return fail("mmd_opt: num_reduced must be in [2, 10]");
         }
@@ -497,7 +508,16 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         else k_rollouts<ROLL_FLY><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
     }
     if (n_launch) *n_launch = 1;
-    if (opt && kind == INNER_PIPE) {
+    if (opt && kind == INNER_BIG) {
+        if (!h->big_state) return fail("internal: large-reduced-set scratch not allocated");
+        int nl = 1;
+        for (int g0 = 0; g0 < r.n_samples; g0 += h->big_chunk) {       // chain ranges share the scratch: launches on one stream run in order
+            const int nc = r.n_samples - g0 < h->big_chunk ? r.n_samples - g0 : h->big_chunk;
+            k_inner_cem_big<<<nc, r.n_samples <= h->sm_count ? BIG_THREADS : 256, 0, s>>>(d, ra, h->big_state, g0, nc);
+            nl++;
+        }
+        if (n_launch) *n_launch = nl;
+    } else if (opt && kind == INNER_PIPE) {
         pipe_kernel(d.nr, h->pipe_minb)<<<(r.n_samples + 1) / 2, ICP_THREADS, pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), s>>>(d, ra, h->throws);
         { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
         if (n_launch) *n_launch = 3;

@@ -386,6 +386,31 @@ def test_inner_cem_repeatable_under_load(mods, monkeypatch, mode):
             _eq(first[k][i], ref[k], f"{mode} chain {i} {k}")
 
 
+@pytest.mark.parametrize("nr,npr,noise,kw,n", [
+    (12, 20, "gaussian", dict(num_samples_cem=40, maxiter_beta_cem=4), 5),
+    (20, 60, "gaussian", dict(num_samples_cem=40, maxiter_beta_cem=3), 4),           # configs[3]: num_reduced 20, num_prime 60
+    (20, 20, "beta", dict(num_samples_cem=100, maxiter_beta_cem=3), 2),              # reference inner-CEM population (100 samples, 11 elites)
+    (40, 20, "gaussian", dict(num_samples_cem=40, maxiter_beta_cem=2), 2)])          # d = 1601: 10 MB covariance per chain
+def test_stage_risk_large_reduced_set_mmd_opt(mods, nr, npr, noise, kw, n):
+    """mmd_opt for num_reduced > 10 (BASELINE configs[3] sweeps {5, 10, 20, 40}): k_inner_cem_big keeps the chain state (distance table nm x nm, covariance
+    (nm+1)^2, samples) in global memory and runs the same phases as the shared-memory kernels -- bit for bit the oracle, which is generic in num_reduced
+    (compute_beta.py:51-68: jnp.cov + multivariate_normal of an (nr^2+1)^2 covariance)."""
+    prob, ora = _pair(mods, (nr, 2, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), **kw)
+    rng = np.random.default_rng(31 + nr)
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(4242, 3)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(2, 5)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    xo = xo.copy(); xo[0] = np.linspace(2, 60, 100); yo = yo.copy(); yo[0] = 1.75
+    got = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(got[k][i], ref[k], f"nr={nr} chain {i} {k}")
+    assert np.isfinite(got["res_beta"]).all()
+
+
 def test_inner_cem_warp_persistent_grid_strides_over_chains(mods, monkeypatch):
     """more chains than persistent CTAs (SMs x resident warps): every CTA of k_inner_cem_warp runs several chains and reuses its stash"""
     monkeypatch.setenv("MPCMMD_INNER_CEM", "warp")
