@@ -193,6 +193,7 @@ def main():
                     help="strong (default, BASELINE's metric): the 200-episode sweep sharded over the ranks; weak: 200 episodes per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE workloads / the weak-scaling value / the batch-1 latency")
+    ap.add_argument("--episodes", type=int, default=0, help="diagnostic: episodes of the sweep (default: the workload's 200); e.g. 25 = one rank's shard of the 8-GPU run")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--projection", default="exact", choices=["exact", "tc"],
                     help="exact = k_project (bit-exact FP32, the default product path); tc = k_project_tc (tcgen05 kind::tf32 products, 1e-4 stage parity)")
@@ -202,6 +203,9 @@ def main():
     else:
         os.environ.pop("MPCMMD_PROJ", None)
     select_workload(args.workload)
+    if args.episodes > 0:
+        global EPISODES
+        EPISODES = args.episodes
     if args.impl == "reference":
         return run_reference(args, emit)
 

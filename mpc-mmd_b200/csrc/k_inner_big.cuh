@@ -10,7 +10,8 @@
 #pragma once
 #include "k_risk.cuh"
 
-#define BIG_THREADS 1024        // upper bound; the host launches 1024 threads when every chain can have an SM to itself, else 256
+#define BIG_THREADS 1024        // launches where every chain can have an SM to itself (<= one chain per SM); larger launches use BIG_THREADS_SMALL
+#define BIG_THREADS_SMALL 256
 struct BigLayout {          // per-chain global state in floats; offsets are multiples of 4
     size_t D, th, cost, betas, idxs, rs, key64, perm, C, mean, eth, xc, ecost, ebetas, eidxs, kscr, small, total;
     int ldc, kstride;
@@ -91,14 +92,15 @@ __device__ __forceinline__ float big_finish(const DCfg& c, int nr, int nm, const
 }
 
 // one CTA per chain; chain g of this launch uses state block (g - g_base) (the host launches chain ranges that fit the scratch budget)
-__global__ void __launch_bounds__(BIG_THREADS) k_inner_cem_big(DCfg c, RollArgs ra, float* __restrict__ state, int g_base, int n_chains) {
+template <int NT>
+__global__ void __launch_bounds__(NT) k_inner_cem_big(DCfg c, RollArgs ra, float* __restrict__ state, int g_base, int n_chains) {
     __shared__ float blk[16];
-    __shared__ float red[3 * MPCMMD_MAX_NR_DEV * (BIG_THREADS / 32)];
+    __shared__ float red[3 * MPCMMD_MAX_NR_DEV * (NT / 32)];
     const RiskArgs& a = ra.r;
     const int g = g_base + blockIdx.x;
     if (blockIdx.x >= n_chains || g >= a.n_samples) return;
     const int nr = c.nr, nm = c.nm, d = nm + 1, np = c.np, S = c.S_in, ne = c.n_el_in, e = g / a.B;
-    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, nt = NT, warp = tid >> 5, lane = tid & 31;
     const BigLayout L = big_layout(nr, S, ne);
     const int ldc = L.ldc;
     float* st = state + (size_t)blockIdx.x * L.total;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_inner_cem_big(DCfg c, RollArgs 
     const int* ridx = (const int*)small + 64;
     const float* xg = ra.xroll + (size_t)g * nm * np; const float* yg = ra.yroll + (size_t)g * nm * np;
     const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
-    const int NW = nt / 32;
+    constexpr int NW = NT / 32;
     for (int r = 0; r < nr; r++) {
         const float* xred = xg + (size_t)ridx[r] * np; const float* yred = yg + (size_t)ridx[r] * np;
         float m = 0.0f, l = 0.0f, u = 0.0f;

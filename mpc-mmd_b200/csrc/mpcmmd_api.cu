@@ -513,7 +513,8 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         int nl = 1;
         for (int g0 = 0; g0 < r.n_samples; g0 += h->big_chunk) {       // chain ranges share the scratch: launches on one stream run in order
             const int nc = r.n_samples - g0 < h->big_chunk ? r.n_samples - g0 : h->big_chunk;
-            k_inner_cem_big<<<nc, r.n_samples <= h->sm_count ? BIG_THREADS : 256, 0, s>>>(d, ra, h->big_state, g0, nc);
+            if (r.n_samples <= h->sm_count) k_inner_cem_big<BIG_THREADS><<<nc, BIG_THREADS, 0, s>>>(d, ra, h->big_state, g0, nc);
+            else k_inner_cem_big<BIG_THREADS_SMALL><<<nc, BIG_THREADS_SMALL, 0, s>>>(d, ra, h->big_state, g0, nc);
             nl++;
         }
         if (n_launch) *n_launch = nl;
