@@ -684,3 +684,276 @@ __global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs 
         a.lane[g] = mmd_cost(c, beta, vals + OPT_RISK_THREADS + tid, sigma) + mmd_cost(c, beta, vals + 2 * OPT_RISK_THREADS + tid, sigma);
     }
 }
+
+// =====================================================================================================================================
+// LATENCY build for launches of at most one chain per SM (batch = 1: 100 chains on 148 SMs; BASELINE's second headline, p50 per-solve latency).
+// With an SM to itself a chain can spread each inner iteration over 16 warps instead of 3: the evaluation is split into (1) top-num_reduced per sample,
+// (2) ONE kernel row sum per thread -- task (sample, reduced index): 25 of the 135 exponentials of a sample -- and (3) the per-sample KKT finish; the
+// resampling runs one task per (row, group of four columns).  Same operations in the same order per element as k_inner_cem_fast (rows of a sample are
+// independent IEEE chains there too), so the bits are unchanged; selection, gather, covariance and the one-warp panel Cholesky are shared code.
+// Phase budget per inner iteration, batch 1: 15 us -> ~9.5 us.
+#define ICL_THREADS 512
+// top-NR |theta| of a row (stable, ascending), packed 5 bits per index: first half of beta_sample_fast
+template <int NR>
+__device__ __forceinline__ int icl_topk(const float* __restrict__ row) {
+    constexpr int nm = NR * NR;
+    int tk[NR + 1];
+#pragma unroll
+    for (int p = 0; p <= NR; p++) tk[p] = 0;
+#pragma unroll
+    for (int m = 0; m < nm; m++) {
+        int v = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m);
+        tk[0] = max(tk[0], v);
+#pragma unroll
+        for (int p = 0; p < NR; p++) { const int lo = min(tk[p], tk[p + 1]), hi = max(tk[p], tk[p + 1]); tk[p] = lo; tk[p + 1] = hi; }
+    }
+    int packed = 0; bool near = false;
+#pragma unroll
+    for (int p = 0; p < NR; p++) { packed |= (tk[p + 1] & 31) << (5 * p); near |= ((tk[p] ^ tk[p + 1]) < 32); }
+    if (near) packed = top_abs_exact<NR>(row);
+    return packed;
+}
+// sum_m exp(-(D[row][m] * rinv)), m ascending, two exponentials per packed evaluation: one lane of beta_eval's row-sum loop
+template <int NR>
+__device__ __forceinline__ float icl_rowsum(const float* __restrict__ Drow, float rinv) {
+    constexpr int nm = NR * NR;
+    const pk::f2 rinv2 = pk::dup(rinv);
+    float rs = 0.0f;
+#pragma unroll 4
+    for (int m = 0; m + 1 < nm; m += 2) {
+        const pk::f2 e = lap2<false>(Drow[m], Drow[m + 1], rinv2);
+        rs = rs + pk::lo(e); rs = rs + pk::hi(e);
+    }
+    if constexpr (nm & 1) rs = rs + pk::lo(lap2<false>(Drow[nm - 1], Drow[nm - 1], rinv2));
+    return rs;
+}
+// reduced kernel, KKT solve and cost of one beta sample from its row sums: second half of beta_eval, operation for operation
+template <int NR>
+__device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sigma, const float* __restrict__ rowsum, const float* __restrict__ D,
+                                            float* __restrict__ beta_out) {
+    constexpr int nm = NR * NR;
+    const float rinv = 1.0f / sigma;
+    const pk::f2 rinv2 = pk::dup(rinv);
+    int ti[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) ti[i] = (packed >> (5 * i)) & 31;
+    float K[NR][NR];
+    {
+        constexpr int NE = NR * (NR - 1) / 2;
+        float dv[NE + 1];
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            K[i][i] = 1.0f;
+#pragma unroll
+            for (int j = 0; j < i; j++) dv[e++] = D[ti[i] * nm + ti[j]];
+        }
+        dv[NE] = dv[NE - 1];
+        float ev[NE + 1];
+#pragma unroll
+        for (int q = 0; q < NE; q += 2) pk::unpack(lap2<false>(dv[q], dv[q + 1], rinv2), ev[q], ev[q + 1]);
+        e = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+#pragma unroll
+            for (int j = 0; j < i; j++) { K[i][j] = ev[e]; K[j][i] = ev[e]; e++; }
+    }
+    float Lm[NR][NR], rd[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        float acc = K[j][j] + 0.05f;
+#pragma unroll
+        for (int k = 0; k < j; k++) acc = fmaf(-Lm[j][k], Lm[j][k], acc);
+        const float dd = sqrtf(acc);
+        Lm[j][j] = dd; rd[j] = 1.0f / dd;
+#pragma unroll
+        for (int i = j + 1; i < NR; i++) {
+            float aa = K[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) aa = fmaf(-Lm[i][k], Lm[j][k], aa);
+            Lm[i][j] = aa * rd[j];
+        }
+    }
+    pk::f2 uw[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        pk::f2 ab = pk::pack(c.inv_nm * rowsum[i], 1.0f);
+#pragma unroll
+        for (int k = 0; k < i; k++) ab = pk::fma2(pk::dup(-Lm[i][k]), uw[k], ab);
+        uw[i] = pk::mul2(ab, pk::dup(rd[i]));
+    }
+#pragma unroll
+    for (int i = NR - 1; i >= 0; i--) {
+        pk::f2 ab = uw[i];
+#pragma unroll
+        for (int k = i + 1; k < NR; k++) ab = pk::fma2(pk::dup(-Lm[k][i]), uw[k], ab);
+        uw[i] = pk::mul2(ab, pk::dup(rd[i]));
+    }
+    float u[NR], w[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) pk::unpack(uw[i], u[i], w[i]);
+    float su = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NR; i++) { su = su + u[i]; sw = sw + w[i]; }
+    const float nu = (su - 1.0f) / sw;
+    float beta[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) beta[i] = fmaf(-nu, w[i], u[i]);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        float t = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NR; j++) t = fmaf(K[i][j], beta[j], t);
+        s1 = fmaf(beta[i], t, s1);
+        s2 = fmaf(c.m2_inv_nm * rowsum[i], beta[i], s2);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) beta_out[i] = beta[i];
+    return s1 + s2;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollArgs ra) {
+    extern __shared__ __align__(128) float sm[];
+    const RiskArgs& a = ra.r;
+    const int g = blockIdx.x;
+    if (g >= a.n_samples) return;
+    constexpr int nm = NR * NR, d = nm + 1, NG = (d + 3) / 4;
+    const int tid = threadIdx.x, nt = ICL_THREADS, warp = tid >> 5, lane = tid & 31;
+    const int S = c.S_in, ne = c.n_el_in;
+    const FastLayout L = fast_layout(NR, S, ne);
+    const int ldt = L.ldt, ldc = L.ldc;
+    float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = ra.bscratch + (size_t)g * S * (NR + 1); int* idxs = (int*)(betas + S * NR);
+    int* perm = (int*)(sm + L.perm); float* xc = sm + L.xc; float* C = sm + L.C; float* LT = C; float* mean = sm + L.mean;
+    float* small = sm + L.small;
+    float* eth = sm + L.eth;
+    float* ecost = sm + L.ecost; float* eb = sm + L.ebetas; int* ei = (int*)(sm + L.eidxs);
+    int* tis = (int*)(sm + L.total); float* rsum = sm + L.total + al4(S);        // per-sample reduced sets (packed) and row sums, behind the shared layout
+    float* zs = rsum + al4(S * NR);                                              // this iteration's resampling normals [column][row], staged while warp 0 factors
+    {   // distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
+        float* F = th;
+        const float* Fg = ra.feat + (size_t)g * nm * 2 * NV;
+#pragma unroll 1
+        for (int i = tid; i < nm * 2 * NV; i += nt) F[i] = Fg[i];
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < nm * nm; i += nt) {
+            const float* Fa = F + (i / nm) * 2 * NV; const float* Fb = F + (i % nm) * 2 * NV;
+            float dist = 0.0f;
+#pragma unroll 2
+            for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
+            D[i] = dist;
+        }
+        __syncthreads();
+    }
+    int cr = -1, cg = 0;                                  // covariance task of this thread (d = 26: 98 tasks <= 512 threads)
+    {
+        int t = 0;
+#pragma unroll 1
+        for (int r = 0; r < d; r++) {
+#pragma unroll 1
+            for (int q4 = 0; q4 <= r / 4; q4++) { if (t == tid) { cr = r; cg = q4; } t++; }
+        }
+    }
+    float* resb = a.res_beta + (size_t)g * c.iters_in;
+#pragma unroll 1
+    for (int it = 0; it < c.iters_in; it++) {
+        const int n_old = it == 0 ? 0 : ne, n_new = S - n_old;
+        const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;
+        // -- evaluation in three phases
+#pragma unroll 1
+        for (int s = tid; s < n_new; s += nt) tis[s] = icl_topk<NR>(rows + s * rstride);
+        __syncthreads();
+#pragma unroll 1
+        for (int task = tid; task < n_new * NR; task += nt) {
+            const int s = task / NR, i = task - s * NR;
+            const float rinv = 1.0f / rows[s * rstride + nm];
+            rsum[task] = icl_rowsum<NR>(D + ((tis[s] >> (5 * i)) & 31) * nm, rinv);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int s = tid; s < n_new; s += nt) {
+            cost[s] = icl_finish<NR>(c, tis[s], rows[s * rstride + nm], rsum + s * NR, D, betas + s * NR);
+            idxs[s] = tis[s];
+        }
+        __syncthreads();
+        if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);
+        __syncthreads();
+        float v[ICF_MAX_NE]; float mu = 0.0f, gb = 0.0f; int gi = 0;
+        if (tid < d) {
+            float s = 0.0f;
+#pragma unroll
+            for (int el = 0; el < ICF_MAX_NE; el++) {
+                if (el < ne) {
+                    const int p = perm[el];
+                    v[el] = p < n_old ? eth[p * ldt + tid] : rows[(p - n_old) * rstride + tid];
+                    s = s + v[el];
+                }
+            }
+            mu = s / (float)ne;
+        } else if (tid >= 32 && tid - 32 < ne * NR) {
+            const int i = tid - 32, p = perm[i / NR], k = i % NR;
+            gb = p < n_old ? eb[p * NR + k] : betas[(p - n_old) * NR + k];
+            if (i < ne) { const int p2 = perm[i]; gi = p2 < n_old ? ei[p2] : idxs[p2 - n_old]; }
+        }
+        __syncthreads();
+        if (tid < d) {
+            mean[tid] = mu;
+#pragma unroll
+            for (int el = 0; el < ICF_MAX_NE; el++) if (el < ne) { eth[el * ldt + tid] = v[el]; xc[el * ldc + tid] = v[el] - mu; }
+        } else if (tid >= 32 && tid - 32 < ne * NR) {
+            eb[tid - 32] = gb;
+            if (tid - 32 < ne) ei[tid - 32] = gi;
+        }
+        __syncthreads();
+        if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
+        __syncthreads();
+        if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
+        else {                                            // the other 15 warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
+            const float* zg = c.zb_iterT + (size_t)it * d * (S - ne);
+#pragma unroll 1
+            for (int i = tid - 32; i < d * (S - ne); i += nt - 32) zs[i] = __ldg(zg + i);
+        }
+        __syncthreads();
+        {   // resample: task = (new row r, group of four columns g4); columns 4 g4 .. 4 g4 + 3 take k = 0 .. 4 g4 + 3 ascending (icf_mvn_row_unrolled's order)
+            const int nrow = S - ne;
+            const float* zT = zs;
+#pragma unroll 1
+            for (int task = tid; task < nrow * NG; task += nt) {
+                const int g4 = task / nrow, r = task - g4 * nrow;
+                const int kend = min(4 * g4 + 3, d - 1);
+                pk::f2 a01 = pk::dup(0.0f), a23 = pk::dup(0.0f);
+#pragma unroll 4
+                for (int k = 0; k <= kend; k++) {
+                    const pk::f2 z2 = pk::dup(zT[k * nrow + r]);
+                    const float4 l = *reinterpret_cast<const float4*>(LT + k * ldc + 4 * g4);
+                    a01 = pk::fma2(pk::pack(l.x, l.y), z2, a01); a23 = pk::fma2(pk::pack(l.z, l.w), z2, a23);
+                }
+                float x[4]; pk::unpack(a01, x[0], x[1]); pk::unpack(a23, x[2], x[3]);
+                float* dst = th + r * ldt + 4 * g4;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int q = 4 * g4 + u;
+                    if (q < d) {
+                        float vv = mean[q] + x[u];
+                        if (q == nm) vv = (vv != vv) ? vv : (vv > c.sigma_clip ? vv : c.sigma_clip);
+                        dst[u] = vv;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            resb[it] = ecost[0];
+            if (it == c.iters_in - 1) {
+                for (int i = 0; i < NR; i++) { small[i] = eb[i]; ((int*)small)[16 + i] = (ei[0] >> (5 * i)) & 31; }
+                const int p0 = perm[0];
+                small[48] = p0 < ne ? eth[p0 * ldt + nm] : th[(p0 - ne) * ldt + nm];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < NR) { a.beta[(size_t)g * NR + tid] = small[tid]; ra.ridx[(size_t)g * NR + tid] = ((const int*)small)[16 + tid]; }
+    if (tid == 0) a.sigma[g] = small[48];
+}

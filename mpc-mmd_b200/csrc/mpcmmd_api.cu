@@ -168,7 +168,7 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
-enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7, INNER_BIG = 8 };
+enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7, INNER_BIG = 8, INNER_LAT512 = 9 };
 #define MPCMMD_BIG_SCRATCH_BYTES ((size_t)8 << 30)      // global chain state of k_inner_cem_big held at a time (num_reduced 40: 23 MB per chain)
 #define INNER_DEFAULT_THROUGHPUT INNER_CTA
 typedef void (*pipe_fn)(DCfg, RollArgs, float*);
@@ -200,6 +200,9 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_CTA) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, false>; case 3: return k_inner_cem_fast<3, false>; case 4: return k_inner_cem_fast<4, false>; case 5: return k_inner_cem_fast<5, false>;
     }
+    if (kind == INNER_LAT512) switch (d.nr) {
+        case 2: return k_inner_cem_lat<2>; case 3: return k_inner_cem_lat<3>; case 4: return k_inner_cem_lat<4>; case 5: return k_inner_cem_lat<5>;
+    }
     if (kind == INNER_CTA_FASTMATH) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, false, true>; case 3: return k_inner_cem_fast<3, false, true>; case 4: return k_inner_cem_fast<4, false, true>; case 5: return k_inner_cem_fast<5, false, true>;
     }
@@ -222,6 +225,7 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
 static size_t inner_cem_smem_kind(const DCfg& d, int kind) {
     if (kind == INNER_WARP) return (size_t)warp_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
     if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) return (size_t)fast_layout(d.nr, d.S_in, d.n_el_in).total * sizeof(float);
+    if (kind == INNER_LAT512) return (size_t)(fast_layout(d.nr, d.S_in, d.n_el_in).total + al4(d.S_in) + al4(d.S_in * d.nr) + al4((d.nm + 1) * (d.S_in - d.n_el_in))) * sizeof(float);
     return (size_t)opt_layout(d.nr, d.np, d.S_in, d.n_el_in).total * sizeof(float);
 }
 
@@ -375,7 +379,7 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
     {
         const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
         h->inner_mode = !mode ? 0 : !strcmp(mode, "warp") ? INNER_WARP : !strcmp(mode, "cta") ? INNER_CTA : !strcmp(mode, "generic") ? INNER_GENERIC :
-                        !strcmp(mode, "lat") ? INNER_CTA_LAT : !strcmp(mode, "split") ? INNER_SPLIT : !strcmp(mode, "pipe") ? INNER_PIPE : 0;
+                        !strcmp(mode, "lat") ? INNER_CTA_LAT : !strcmp(mode, "split") ? INNER_SPLIT : !strcmp(mode, "pipe") ? INNER_PIPE : !strcmp(mode, "lat512") ? INNER_LAT512 : 0;
         if (!inner_cem_is_fast(d) && h->inner_mode != 0) h->inner_mode = INNER_GENERIC;
         if (inner_cem_is_fast(d)) {
             const SplitKernels sk = split_kernels(d.nr);
@@ -387,8 +391,8 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
             if (raise_smem(device, (const void*)pipe_kernel(d.nr, h->pipe_minb), pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), true)) return fail("k_inner_cem_pipe smem opt-in failed");
         }
         { const char* mm = getenv("MPCMMD_MATH"); h->fast_math = mm && !strcmp(mm, "fast"); }
-        for (int kind = INNER_WARP; kind <= INNER_CTA_FASTMATH; kind++) {
-            if (kind == INNER_SPLIT || kind == INNER_PIPE) continue;
+        for (int kind = INNER_WARP; kind <= INNER_LAT512; kind++) {
+            if (kind == INNER_SPLIT || kind == INNER_PIPE || kind == INNER_BIG) continue;
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
             inner_cem_fn f = inner_cem_kernel(d, kind);
             if (!f) continue;
@@ -485,7 +489,8 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         // 19 independent instruction streams per SM thrash the 32 KB instruction cache.
         // a launch that fits in one wave of resident CTAs (e.g. a single episode) is latency-bound: take the build with the 96-register budget
         // a launch of at most 3 chains per SM (one episode = 100 chains) is pure dependency latency: the latency build of the fused kernel
-        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= 3 * h->sm_count ? INNER_CTA_LAT : INNER_DEFAULT_THROUGHPUT);
+        // (at most one chain per SM: the 16-warp latency kernel k_inner_cem_lat; up to 3 per SM: the 3-warp latency build of the fused kernel)
+        if (inner_cem_is_fast(d)) kind = h->inner_mode ? h->inner_mode : (r.n_samples <= h->sm_count ? INNER_LAT512 : r.n_samples <= 3 * h->sm_count ? INNER_CTA_LAT : INNER_DEFAULT_THROUGHPUT);
         if (d.nr > MPCMMD_MAX_NR) kind = INNER_BIG;
         if (kind == INNER_PIPE && !pipe_ok(d)) kind = INNER_CTA;
         if (kind == INNER_CTA && h->fast_math) kind = INNER_CTA_FASTMATH;
@@ -496,7 +501,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         }
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
-        if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_CTA_FASTMATH && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
+        if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_CTA_FASTMATH && kind != INNER_LAT512 && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
             if (!h->rolls_x) return fail("internal: mother-rollout scratch not allocated");
             ra.write_rolls = 1; ra.xroll = h->rolls_x; ra.yroll = h->rolls_y;
         }
@@ -539,9 +544,9 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     } else if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
         if (kind == INNER_WARP) f<<<r.n_samples < h->warp_grid ? r.n_samples : h->warp_grid, 32, sm, s>>>(d, ra);
-        else f<<<r.n_samples, (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
+        else f<<<r.n_samples, kind == INNER_LAT512 ? ICL_THREADS : (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
-        if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) {
+        if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH || kind == INNER_LAT512) {
             { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
             if (n_launch) *n_launch = 3;
         }
@@ -688,7 +693,7 @@ extern "C" const char* mpcmmd_inner_cem_path(mpcmmd_handle h) {
         case INNER_GENERIC: return "k_inner_cem (generic, one CTA per chain)";
         default: return INNER_DEFAULT_THROUGHPUT == INNER_PIPE
                             ? "k_inner_cem_pipe (two chains per CTA: 3 evaluation warps + 1 serial warp); launches of <= 3 chains per SM: k_inner_cem_fast<LAT>"
-                            : "k_inner_cem_fast (one CTA per chain); launches of <= 3 chains per SM: its latency build";
+                            : "k_inner_cem_fast (one CTA per chain); launches of <= 3 chains per SM: its latency build; <= 1 chain per SM: k_inner_cem_lat (16 warps per chain)";
     }
 }
 

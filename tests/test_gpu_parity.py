@@ -336,7 +336,7 @@ def test_stage_select_bit_exact(mods):
 
 
 # ---- the three inner-CEM kernels (k_inner_cem_warp: one warp per chain, persistent; k_inner_cem_fast: one CTA per chain; k_inner_cem: generic)
-@pytest.mark.parametrize("mode", ["pipe", "split", "warp", "cta", "lat", "generic"])
+@pytest.mark.parametrize("mode", ["lat512", "pipe", "split", "warp", "cta", "lat", "generic"])
 @pytest.mark.parametrize("nr,npr,noise,small", [(5, 30, "gaussian", True), (5, 50, "beta", False), (4, 20, "gaussian", True), (3, 20, "beta", True), (2, 25, "gaussian", True)])
 def test_inner_cem_kernel_variants_bit_exact(mods, monkeypatch, mode, nr, npr, noise, small):
     monkeypatch.setenv("MPCMMD_INNER_CEM", mode)
