@@ -20,6 +20,7 @@ struct DCfg {
     float wheel_base, dt, steer_max, steer_rate_pen, alpha_quant, ker_wt;
     float lam_inv, one_m_alpha_mean, alpha_mean, one_m_alpha_cov, alpha_cov;
     float sigma_clip, inv_nm, m2_inv_nm, beta_del, sigma_random;
+    float obs_win;                                           // half-width of the x window outside of which the obstacle indicator is exactly 0: sqrt(a2_obs) + 0.01
     const float *P, *Pd, *Pdd, *Gx, *Gy, *Kx, *Ky, *Wfit;   // device copies of the host constants
     const float* proj_const;                                 // P | Pd | Pdd | Gx | Gy | Kx | Ky as ONE 16-byte-aligned block (bulk-copied into shared memory by k_project)
     const float* proj_tc_const;                              // tf32 (hi, lo) images of P / Pd / Pdd + Gx | Gy | Kx | Ky for k_project_tc
@@ -48,6 +49,8 @@ struct DWork {
     float *init_state;             // [E][6]
     float *mean0, *cov0;           // [E][8], [E][64]
     float *x_obs, *y_obs;          // [E][O][100]
+    float *sx_obs, *sy_obs;        // [E][100][O]  obstacle positions per knot, sorted by x (k_obs_sort; only for num_obs > OBS_SORT_MIN, else null)
+    int *obs_nan;                  // [E][100]     1 if a coordinate of that knot is NaN (then the plain loop runs)
     float *v_des;                  // [E]
     // staged outputs
     float *o_cx, *o_cy, *o_lane, *o_obs, *o_beta, *o_sigma, *o_res_beta;

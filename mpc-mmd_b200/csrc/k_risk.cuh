@@ -25,6 +25,8 @@ struct RiskArgs {
     size_t btab_stride;
     const float *binj1, *binj2;      // [n][nr*np] injected Beta draws (acceleration, steering) instead of the device sampler; null in solves (mpcmmd_stage_risk_injected)
     const float *x_obs, *y_obs;      // [E][O][100]
+    const float *sx_obs, *sy_obs;    // [E][100][O] sorted by x per knot, or null (plain obstacle loop)
+    const int* obs_nan;              // [E][100]
     float *risk, *lane;              // [n]
     float *beta, *sigma, *res_beta;  // [n][nr], [n], [n][iters_in]
 };
@@ -205,6 +207,30 @@ __device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, 
     sn = (sv + ps) + c.steer_const * z3[el];
 }
 
+// Many obstacles (configs[4]: 32): the indicator of obstacle o at knot t is exactly 0 unless |x - xo| < a_obs (fbar's screen: A >= a^2 makes the rounded
+// cost <= 0), so only the obstacles inside an x window around the vehicle can raise the maximum.  k_obs_sort orders every knot's obstacles by x once
+// per solve; the rollout binary-searches the window (2-5 obstacles instead of 32).  Exact: the window is 0.01 m wider than a_obs (rounding of
+// x +- w at |x| < 1e4 is < 5e-4), skipped obstacles contribute exactly 0, and the maximum is order independent; NaN positions (vehicle or
+// obstacle) and |x| >= 1e4 take the plain loop, so NaN propagation is unchanged.
+#define OBS_SORT_MIN 8
+__global__ void k_obs_sort(const float* __restrict__ x_obs, const float* __restrict__ y_obs, float* __restrict__ sx, float* __restrict__ sy,
+                           int* __restrict__ nan_flag, int O, int n_knots /* = n_ep * 100 */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_knots) return;
+    const int e = i / T_, t = i % T_;
+    float xs[MPCMMD_MAX_NR_DEV], ys[MPCMMD_MAX_NR_DEV];
+    int bad = 0;
+    for (int o = 0; o < O; o++) {                     // stable insertion sort by x (NaN last)
+        const float xv = x_obs[((size_t)e * O + o) * T_ + t], yv = y_obs[((size_t)e * O + o) * T_ + t];
+        bad |= (xv != xv) || (yv != yv);
+        int j = o;
+        while (j > 0 && dm::lt_nanlast(xv, xs[j - 1])) { xs[j] = xs[j - 1]; ys[j] = ys[j - 1]; j--; }
+        xs[j] = xv; ys[j] = yv;
+    }
+    for (int o = 0; o < O; o++) { sx[(size_t)i * O + o] = xs[o]; sy[(size_t)i * O + o] = ys[o]; }
+    nan_flag[i] = bad;
+}
+
 // one rollout with its obstacle / lane indicators folded in: m = max over (obstacle, t) of f_bar, l / u = max over t of the lane violations,
 // each evaluated on the state BEFORE step t (the recorded point).  The maxima are order independent (NaN propagates either way), so this equals
 // the reference's "roll out, then reduce" [costs.py:50-71].  FLY: the controls of row `row` are drawn inside the loop (costs with one control row
@@ -219,8 +245,21 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
     for (int t = 0; t < np; t++) {
         float at, st;
         if (FLY) { noisy_control(c, A, g, e, row * np + t, t, n, at, st); st = dm::tan_(st); } else { at = a[t]; st = s[t]; }      // s = tan(steer) when staged
+        if (A.sx_obs && x == x && y == y && fabsf(x) < 1.0e4f && !A.obs_nan[e * T_ + t]) {
+            const float* xs = A.sx_obs + ((size_t)e * T_ + t) * c.O; const float* ys = A.sy_obs + ((size_t)e * T_ + t) * c.O;
+            const float xl = x - c.obs_win, xh = x + c.obs_win;
+            int lo = 0, n_ = c.O;
+            while (n_ > 0) { const int half = n_ >> 1; if (xs[lo + half] <= xl) { lo += half + 1; n_ -= half + 1; } else n_ = half; }     // first obstacle with xs > x - w
+#pragma unroll 1
+            for (int i = lo; i < c.O; i++) {
+                const float xv = xs[i];
+                if (!(xv < xh)) break;
+                m = dm::nmax_(m, fbar(c, x, y, xv, ys[i]));
+            }
+        } else {
 #pragma unroll 4
-        for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+            for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+        }
         l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
         u = dm::nmax_(u, dm::max0_(y - c.y_ub));
         bicycle_step(c, at, st, x, y, vx, vy, psi);

@@ -561,6 +561,38 @@ def test_solve_scaled_batch_bit_exact(mods, cost, noise, B, kw):
             _eq(got[k][e], ref[k], f"B={B} {cost} ep{e} {k}")
 
 
+@pytest.mark.parametrize("cost,nobs,special", [("cvar", 32, "plain"), ("cvar", 32, "nan_obstacle"), ("mmd_random", 20, "moving"), ("mmd_opt", 32, "edge"),
+                                               ("cvar", 64, "plain")])
+def test_stage_risk_many_obstacles_sorted_window(mods, cost, nobs, special):
+    """num_obs > 8 (configs[4]: 32 obstacles): the rollouts look only at the obstacles inside an x window around the vehicle, found by binary search in the
+    per-knot sorted obstacle lists of k_obs_sort.  Skipped obstacles contribute exactly 0, so the result must equal the oracle's all-pairs maximum bit for bit --
+    with static and moving obstacles, with obstacles placed right at the window edge (|dx| = a_obs +- ulps), and with a NaN obstacle coordinate (plain-loop fallback)."""
+    kw = dict(num_samples_cem=40, maxiter_beta_cem=3) if cost == "mmd_opt" else {}
+    prob, ora = _pair(mods, (5, nobs, 0.1, 60, "gaussian", 0.02, 0.01), max_episodes=1, **kw)
+    rng = np.random.default_rng(300 + nobs)
+    n = 24 if cost != "mmd_opt" else 6
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(91, 4)
+    t = np.linspace(0.0, 15.0, 100).astype(f32)
+    x0 = rng.uniform(3.0, 90.0, nobs).astype(f32); y0 = rng.choice([-1.75, 1.75], nobs).astype(f32)
+    vx = (rng.uniform(0.0, 6.0, nobs) if special == "moving" else np.zeros(nobs)).astype(f32)
+    xo = (x0[:, None] + vx[:, None] * t[None]).astype(f32); yo = np.repeat(y0[:, None], 100, 1).astype(f32)
+    if special == "edge":          # obstacles exactly a_obs = 4.25 (and one ulp either side) ahead of where a nominal rollout is at knots 5, 10, 15
+        xr = ora.risk("cvar", acc[0], steer[0], st0, noise_t, xo, yo, want_rollouts=True)["x_roll"][0]
+        for j, (kn, du) in enumerate(((5, 0), (10, 1), (15, -1), (20, 2))):
+            xe = np.nextafter(f32(xr[kn] + 4.25), f32(np.inf) if du > 0 else f32(-np.inf)) if du else f32(xr[kn] + 4.25)
+            xo[j, :] = xe; yo[j, :] = 1.75
+    if special == "nan_obstacle":
+        xo[3, 17] = np.nan; yo[5, 40] = np.nan
+    got = prob.stage_risk(cost, acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk(cost, acc[i], steer[i], st0, noise_t, xo, yo)
+        _eq(got["risk"][i], ref["risk"], f"{special} risk[{i}]"); _eq(got["lane"][i], ref["lane"], f"{special} lane[{i}]")
+    if special != "nan_obstacle":
+        assert np.isfinite(got["risk"]).all() and np.any(got["risk"] != got["risk"][0])
+
+
 @pytest.mark.parametrize("nr,npr", [(10, 20), (20, 60), (40, 100), (40, 20)])
 @pytest.mark.parametrize("cost", ["mmd_random", "cvar"])
 def test_stage_risk_large_reduced_sets(mods, cost, nr, npr):
