@@ -356,8 +356,9 @@ __device__ __forceinline__ void icf_chol(float* __restrict__ C, int ldc, int lan
 // untouched part of C's lower triangle still holds the covariance; each lane zeroes its consumed sub-diagonal entries, which is the zero
 // fill the resampling loops rely on (LT[k][q] = 0 for q < k).
 template <int d>
-__device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc, int lane) {
-    constexpr int NG = (d + 3) / 4;
+__device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc_, int lane) {
+    constexpr int NG = (d + 3) / 4, ldc = (d + 3) & ~3;    // the row stride is a compile-time constant (every caller passes al4(d)): immediate load offsets
+    (void)ldc_;
     const int r = lane < d ? lane : d - 1;                 // lanes >= d shadow the last row (no stores)
     float* rowp = C + r * ldc;
 #pragma unroll 1
@@ -365,11 +366,19 @@ __device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc, i
         const int j0 = 4 * p;
         float4 av = *reinterpret_cast<const float4*>(rowp + j0);          // a(r, j0..j0+3)
         float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
-#pragma unroll 4
-        for (int k = 0; k < j0; k++) {
-            const float lr = C[k * ldc + r];                               // LT[k][r] = L[r][k]
-            const float4 lj = *reinterpret_cast<const float4*>(C + k * ldc + j0);   // L[j0..j0+3][k]
-            a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+        {
+            const float* pr = C + r;                                       // LT[k][r] = L[r][k], k = 0, 1, ...
+            const float* pj = C + j0;                                      // L[j0..j0+3][k]
+#pragma unroll 1
+            for (int k4 = 0; k4 < p; k4++) {                               // j0 is a multiple of four: whole groups of four columns, fixed offsets
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float lr = pr[u * ldc];
+                    const float4 lj = *reinterpret_cast<const float4*>(pj + u * ldc);
+                    a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+                }
+                pr += 4 * ldc; pj += 4 * ldc;
+            }
         }
         // diagonal block b(u', u), u <= u', from lanes j0 + u'
         const float b00 = __shfl_sync(FULL, a0, j0);
