@@ -142,7 +142,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True); self._th.start(); return self
