@@ -680,8 +680,9 @@ __global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs 
         const int e = g / a.B, mi = ra.ridx[(size_t)g * nr + r];
         const float* ct = ra.ctrl + (size_t)g * 2 * n;
         float m, l, u;
-        rollout_risk<false>(c, a, g, e, 0, ct + (mi / nr) * np, ct + n + (mi % nr) * np, a.state0 + e * 5,
-                            a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
+        if (ra.fold_risk) { const float* mr = ra.mrisk + ((size_t)g * nr * nr + mi) * 3; m = mr[0]; l = mr[1]; u = mr[2]; }     // folded by the mother rollout itself
+        else rollout_risk<false>(c, a, g, e, 0, ct + (mi / nr) * np, ct + n + (mi % nr) * np, a.state0 + e * 5,
+                                 a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
         vals[tid] = m; vals[OPT_RISK_THREADS + tid] = l; vals[2 * OPT_RISK_THREADS + tid] = u;
     }
     __syncthreads();

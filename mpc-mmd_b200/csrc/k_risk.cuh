@@ -57,23 +57,34 @@ __device__ __forceinline__ void bicycle_step(const DCfg& c, float a, float ts, f
 // rollout of a mother sample of mmd_opt: the 22 ridge-fit features (cem_helper.py:553-564, folded: feature_k = sum_t Wfit[k][t] * x[t],
 // ascending t -- the contract's order) are accumulated while the state advances; the 22 independent fma chains fill the issue slots the
 // serial sqrt -> tan -> sincos chain leaves empty.  Positions are written only for the kernels that still read them back (WRITE).
-template <bool WRITE>
+// MODE 0: features only; 1: also write the positions (kernels that read the mother rollouts back); 2: also fold the rollout's obstacle / lane maxima
+// (latency regime: k_opt_risk then picks the chosen rollouts' maxima instead of re-rolling them -- same values, the maxima are order independent)
+template <int MODE>
 __device__ __forceinline__ void rollout_fit(const DCfg& c, const float* a, const float* s, const float* st0, const float* __restrict__ W /* (11,np) */,
-                                            float* __restrict__ xg, float* __restrict__ yg, float* __restrict__ feat) {
+                                            float* __restrict__ xg, float* __restrict__ yg, float* __restrict__ feat,
+                                            const float* __restrict__ xo = nullptr, const float* __restrict__ yo = nullptr, float* __restrict__ mr = nullptr) {
     float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
     float fx[NV], fy[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) { fx[k] = 0.0f; fy[k] = 0.0f; }
+    float m = 0.0f, l = 0.0f, u = 0.0f;
     const int np = c.np;
 #pragma unroll 1
     for (int t = 0; t < np; t++) {          // the state BEFORE step t is the recorded point  [cem_helper.py:451-458]
-        if (WRITE) { xg[t] = x; yg[t] = y; }
+        if (MODE == 1) { xg[t] = x; yg[t] = y; }
 #pragma unroll
         for (int k = 0; k < NV; k++) { const float w = W[k * np + t]; fx[k] = fmaf(w, x, fx[k]); fy[k] = fmaf(w, y, fy[k]); }
+        if (MODE == 2) {
+#pragma unroll 4
+            for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+            l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+            u = dm::nmax_(u, dm::max0_(y - c.y_ub));
+        }
         bicycle_step(c, a[t], s[t], x, y, vx, vy, psi);          // s = tan(steer), see k_rollouts
     }
 #pragma unroll
     for (int k = 0; k < NV; k++) { feat[k] = fx[k]; feat[NV + k] = fy[k]; }
+    if (MODE == 2) { mr[0] = m; mr[1] = l; mr[2] = u; }
 }
 // Laplace-kernel MMD of nr scalar costs against the zero cost  [kernel_computation.py:67-87]
 __device__ __noinline__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, float sigma) {
@@ -165,6 +176,8 @@ struct RollArgs {
     int R;                   // rollouts per sample (nr or nr*nr)
     int stage_ctrl;          // cvar / saa / mmd_random: draw the noisy controls into shared memory with the whole CTA first (latency regime: few samples)
     int write_rolls;         // mmd_opt: also write the mother rollouts (only the generic / warp-per-chain inner kernels read them back)
+    int fold_risk;           // mmd_opt, small launches: the mother rollouts also fold their obstacle / lane maxima into mrisk, k_opt_risk does not re-roll
+    float* mrisk;            // [n][nm][3]
     float *xroll, *yroll;    // [n][R][np]   (mmd_opt, write_rolls only)
     float* feat;             // [n][nm][22]  (mmd_opt only)
     float* ctrl;             // [n][2][nr*np]  noisy acceleration and tan(noisy steering) of the sample (mmd_opt): k_opt_risk re-rolls the chosen reduced set from them
@@ -297,8 +310,10 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
             const float* an = sm + ls * 2 * n + (m / nr) * np; const float* sn = sm + ls * 2 * n + n + (m % nr) * np;
             float* ft = ra.feat + ((size_t)g * R + m) * 2 * NV;
-            if (ra.write_rolls) rollout_fit<true>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
-            else rollout_fit<false>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft);
+            if (ra.write_rolls) rollout_fit<1>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
+            else if (ra.fold_risk) rollout_fit<2>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft, a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_,
+                                                  ra.mrisk + ((size_t)g * R + m) * 3);
+            else rollout_fit<0>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft);
         }
     } else {
     // ================= cvar / saa / mmd_random: one thread per (sample, rollout), controls drawn inside the rollout =================

@@ -55,6 +55,7 @@ struct mpcmmd_handle_s {
     int* ridx = nullptr;       // [E*B][nr] reduced sets (k_inner_cem_fast -> k_opt_risk)
     float* bscratch = nullptr; // [E*B][S][nr+1] row records of k_inner_cem_fast
     float* ctrl = nullptr;     // [E*B][2][nr*np] noisy controls (k_rollouts -> k_opt_risk)
+    float* mrisk = nullptr;         // [E*B][nm][3] obstacle / lane maxima of the mother rollouts (small mmd_opt launches: RollArgs::fold_risk)
     float* throws = nullptr;        // [E*B][nm+1][ICP_TH_LD] candidate-elite rows of the pipelined inner CEM (k_inner_pipe.cuh)
     int pipe_minb = 8;              // CTAs per SM the pipelined kernel is compiled for (MPCMMD_PIPE_MINB=8|9|12)
     float* big_state = nullptr;     // [big_chunk][BigLayout::total] chain blocks of k_inner_cem_big (num_reduced > 10), reused by successive chain ranges
@@ -80,9 +81,9 @@ struct mpcmmd_handle_s {
 
 // ---- episode-offset view of a handle's workspace: every per-episode array advanced by e0 episodes.  A solve graph can then enqueue disjoint episode
 // ranges on different streams with the unchanged launch code (episodes are independent; sample index g and episode index e stay relative to the view).
-struct ViewSave { DWork w; float *beq_x, *beq_y, *state0, *feat, *ctrl, *bscratch, *throws, *split_state, *rolls_x, *rolls_y, *xroll; int* ridx; };
+struct ViewSave { DWork w; float *beq_x, *beq_y, *state0, *feat, *ctrl, *bscratch, *throws, *split_state, *rolls_x, *rolls_y, *xroll, *mrisk; int* ridx; };
 static ViewSave push_view(mpcmmd_handle_s* h, int e0) {
-    ViewSave sv = {h->w, h->beq_x, h->beq_y, h->state0, h->feat, h->ctrl, h->bscratch, h->throws, h->split_state, h->rolls_x, h->rolls_y, h->xroll, h->ridx};
+    ViewSave sv = {h->w, h->beq_x, h->beq_y, h->state0, h->feat, h->ctrl, h->bscratch, h->throws, h->split_state, h->rolls_x, h->rolls_y, h->xroll, h->mrisk, h->ridx};
     if (e0 == 0) return sv;
     const DCfg& d = h->d; DWork& w = h->w;
     const size_t e = (size_t)e0, B = d.B, n = (size_t)d.nr * d.np, ncem = (size_t)(d.B - d.n_el) * NPAR, it = d.iters;
@@ -97,14 +98,14 @@ static ViewSave push_view(mpcmmd_handle_s* h, int e0) {
     ADV(h->beq_x, 3); ADV(h->beq_y, 4); ADV(h->state0, 5);
     ADV(h->feat, B * d.nm * 2 * NV); ADV(h->ctrl, B * 2 * n); ADV(h->ridx, B * d.nr); ADV(h->bscratch, B * d.S_in * (d.nr + 1));
     ADV(h->throws, B * (d.nm + 1) * ICP_TH_LD); ADV(h->split_state, B * (size_t)split_layout(d.nr, d.S_in, d.n_el_in).total);
-    ADV(h->rolls_x, B * d.nm * d.np); ADV(h->rolls_y, B * d.nm * d.np);
+    ADV(h->rolls_x, B * d.nm * d.np); ADV(h->rolls_y, B * d.nm * d.np); ADV(h->mrisk, B * d.nm * 3);
     if (h->xroll) h->xroll = h->feat;
 #undef ADV
     return sv;
 }
 static void pop_view(mpcmmd_handle_s* h, const ViewSave& sv) {
     h->w = sv.w; h->beq_x = sv.beq_x; h->beq_y = sv.beq_y; h->state0 = sv.state0; h->feat = sv.feat; h->ctrl = sv.ctrl; h->bscratch = sv.bscratch;
-    h->throws = sv.throws; h->split_state = sv.split_state; h->rolls_x = sv.rolls_x; h->rolls_y = sv.rolls_y; h->xroll = sv.xroll; h->ridx = sv.ridx;
+    h->throws = sv.throws; h->split_state = sv.split_state; h->rolls_x = sv.rolls_x; h->rolls_y = sv.rolls_y; h->xroll = sv.xroll; h->mrisk = sv.mrisk; h->ridx = sv.ridx;
 }
 
 template <typename Tp>
@@ -473,6 +474,7 @@ static int ensure_opt_scratch(mpcmmd_handle_s* h) {
     }
     if (dalloc(h, &h->ridx, EB * d.nr)) return -1;
     if (inner_cem_is_fast(d) && dalloc(h, &h->bscratch, EB * d.S_in * (d.nr + 1))) return -1;
+    if (inner_cem_is_fast(d) && dalloc(h, &h->mrisk, EB * d.nm * 3)) return -1;
     if (inner_cem_is_fast(d) && dalloc(h, &h->throws, EB * (d.nm + 1) * ICP_TH_LD)) return -1;
     if (inner_cem_is_fast(d) && dalloc(h, &h->split_state, EB * split_layout(d.nr, d.S_in, d.n_el_in).total)) return -1;
     if (inner_cem_is_fast(d) && h->warp_grid > 0 && dalloc(h, &h->stash, (size_t)h->warp_grid * d.S_in * ICW_STASH_LD)) return -1;
@@ -485,7 +487,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     const bool opt = r.cost_kind == MPCMMD_COST_MMD_OPT;
     if (r.n_samples > h->E * d.B) return fail("risk stage: more samples than the workspace holds (max_episodes * num_batch)");
     RollArgs ra;
-    ra.r = r; ra.spb = roll_spb(h, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch; ra.ctrl = h->ctrl; ra.write_rolls = 0; ra.stage_ctrl = roll_stage_ctrl(h, r.cost_kind, r.n_samples);
+    ra.r = r; ra.spb = roll_spb(h, r.cost_kind, r.n_samples); ra.R = opt ? d.nm : d.nr; ra.xroll = h->xroll; ra.yroll = h->yroll; ra.feat = h->feat; ra.stash = nullptr; ra.ridx = h->ridx; ra.bscratch = h->bscratch; ra.ctrl = h->ctrl; ra.write_rolls = 0; ra.fold_risk = 0; ra.mrisk = h->mrisk; ra.stage_ctrl = roll_stage_ctrl(h, r.cost_kind, r.n_samples);
     inner_cem_fn f = nullptr;
     int kind = INNER_GENERIC;
     if (opt) {
@@ -506,6 +508,10 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         }
         if (!h->xroll) return fail("internal: mmd_opt scratch not allocated");
         ra.stash = h->stash;
+        // latency regime (at most 3 chains per SM): the serial rollout recurrence is the cost of every kernel, so k_opt_risk's re-roll of the chosen reduced set is
+        // replaced by maxima the mother rollouts fold in themselves (mmd_opt p50 at batch 1: 6.79 -> 6.57 ms).  Larger launches keep the re-roll: the extra
+        // obstacle work in k_rollouts (+20 %) costs more than the short k_opt_risk it removes (measured at 13 / 25 / 50 episodes: 14.4 / 22.9 / 41.8 ms vs 14.7 / 24.0 / 42.4)
+        if (kind != INNER_GENERIC && kind != INNER_WARP && kind != INNER_BIG && h->mrisk && d.O <= OBS_SORT_MIN && r.n_samples <= 3 * h->sm_count) ra.fold_risk = 1;
         if (kind != INNER_CTA && kind != INNER_CTA_LAT && kind != INNER_CTA_FASTMATH && kind != INNER_LAT512 && kind != INNER_SPLIT && kind != INNER_PIPE) {          // these kernels evaluate the risk themselves from the stored mother rollouts
             if (!h->rolls_x) return fail("internal: mother-rollout scratch not allocated");
             ra.write_rolls = 1; ra.xroll = h->rolls_x; ra.yroll = h->rolls_y;
