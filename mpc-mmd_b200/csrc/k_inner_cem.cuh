@@ -686,12 +686,39 @@ __global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs 
         vals[tid] = m; vals[OPT_RISK_THREADS + tid] = l; vals[2 * OPT_RISK_THREADS + tid] = u;
     }
     __syncthreads();
-    if (live && r == 0) {
-        float beta[MPCMMD_MAX_NR];
-        for (int i = 0; i < nr; i++) beta[i] = a.beta[(size_t)g * nr + i];
+    // the three Laplace-kernel MMD values of the sample [kernel_computation.py:67-87]: thread r evaluates kernel row r of each (ascending-j fma chains, 3 (nr + 1)
+    // exponentials instead of 3 nr (nr + 1) on one thread), thread 0 of the sample folds the rows in ascending i -- the operations of mmd_cost in the same order
+    __shared__ float rows_t[3 * OPT_RISK_THREADS], rows_u[3 * OPT_RISK_THREADS];
+    if (live) {
         const float sigma = a.sigma[g];
-        a.risk[g] = mmd_cost(c, beta, vals + tid, sigma);
-        a.lane[g] = mmd_cost(c, beta, vals + OPT_RISK_THREADS + tid, sigma) + mmd_cost(c, beta, vals + 2 * OPT_RISK_THREADS + tid, sigma);
+        const int base = tid - r;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const float* cst = vals + q * OPT_RISK_THREADS + base;
+            const float ci = cst[r];
+            float t = 0.0f;
+            for (int j = 0; j < nr; j++) t = fmaf(dm::exp_(-fabsf(ci - cst[j]) / sigma), a.beta[(size_t)g * nr + j], t);
+            const float e = dm::exp_(-fabsf(ci - 0.0f) / sigma);
+            float u = 0.0f;
+            for (int j = 0; j < nr; j++) u = fmaf(e, c.beta_del, u);
+            rows_t[q * OPT_RISK_THREADS + tid] = t; rows_u[q * OPT_RISK_THREADS + tid] = u;
+        }
+    }
+    __syncthreads();
+    if (live && r == 0) {
+        float res[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            float s1 = 0.0f, s2 = 0.0f;
+            for (int i = 0; i < nr; i++) {
+                const float bi = a.beta[(size_t)g * nr + i];
+                s1 = fmaf(bi, rows_t[q * OPT_RISK_THREADS + tid + i], s1);
+                s2 = fmaf(bi, rows_u[q * OPT_RISK_THREADS + tid + i], s2);
+            }
+            res[q] = c.ker_wt * (s1 - 2.0f * s2);
+        }
+        a.risk[g] = res[0];
+        a.lane[g] = res[1] + res[2];
     }
 }
 
@@ -823,6 +850,104 @@ __device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sig
     return s1 + s2;
 }
 
+// Two-warp panel Cholesky with LOOK-AHEAD (latency kernel only).  Entry (r, j) of panel p accumulates fma(-L_rk, L_jk, .) over k = 0 .. j0-1 ascending; the terms
+// k < j0 - 4 use columns that were final one panel earlier, so warp 1 computes them for panel p + 1 (all rows, partial sums into a double-buffered 26 x 4
+// shared array) while warp 0 gathers, factors and writes panel p.  Warp 0's critical path keeps only the four newest columns of the k loop, the 4 x 4 block chain and
+// the stores.  Same per-entry operation order as icf_chol_panel => same bits.  Named barriers 1/2 (partial sums of an even / odd panel ready: warp 1 arrives,
+// warp 0 waits) and 3/4 (columns of an even / odd panel written: warp 0 arrives, warp 1 waits), 64 participants each; immediates, see k_inner_pipe.cuh.
+template <int ID> __device__ __forceinline__ void icl_bar_sync64() { asm volatile("bar.sync %0, 64;" :: "n"(ID) : "memory"); }
+template <int ID> __device__ __forceinline__ void icl_bar_arrive64() { asm volatile("bar.arrive %0, 64;" :: "n"(ID) : "memory"); }
+template <int d>
+__device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float* __restrict__ ps /* [2][32][4] */, int warp, int lane) {
+    constexpr int NG = (d + 3) / 4, ldc = (d + 3) & ~3;
+    const int r = lane < d ? lane : d - 1;
+    float* rowp = C + r * ldc;
+    if (warp == 1) {
+        // partial sums of panel p (p >= 2) over the columns k < 4 (p - 1): needs panel p - 2 written
+#pragma unroll 1
+        for (int p = 2; p < NG; p++) {
+            if ((p & 1) == 0) icl_bar_sync64<3>(); else icl_bar_sync64<4>();          // panel p - 2 (same parity) is in place
+            const int j0 = 4 * p;
+            const float4 av = *reinterpret_cast<const float4*>(rowp + j0);
+            float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
+            const float* pr = C + r; const float* pj = C + j0;
+#pragma unroll 1
+            for (int k4 = 0; k4 < p - 1; k4++) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float lr = pr[u * ldc];
+                    const float4 lj = *reinterpret_cast<const float4*>(pj + u * ldc);
+                    a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+                }
+                pr += 4 * ldc; pj += 4 * ldc;
+            }
+            *reinterpret_cast<float4*>(ps + ((p & 1) * 32 + lane) * 4) = make_float4(a0, a1, a2, a3);
+            __threadfence_block();
+            __syncwarp();
+            if ((p & 1) == 0) icl_bar_arrive64<1>(); else icl_bar_arrive64<2>();
+        }
+        return;
+    }
+    // warp 0: the panels
+#pragma unroll 1
+    for (int p = 0; p < NG; p++) {
+        const int j0 = 4 * p;
+        const float4 av = *reinterpret_cast<const float4*>(rowp + j0);          // a(r, j0..j0+3): needed for the zero fill below even when the sums come from warp 1
+        float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
+        if (p >= 2) {
+            if ((p & 1) == 0) icl_bar_sync64<1>(); else icl_bar_sync64<2>();
+            const float4 pv = *reinterpret_cast<const float4*>(ps + ((p & 1) * 32 + lane) * 4);
+            a0 = pv.x; a1 = pv.y; a2 = pv.z; a3 = pv.w;
+        }
+        if (p >= 1) {                                                             // the four newest columns k = j0 - 4 .. j0 - 1
+            const float* pr = C + (j0 - 4) * ldc + r; const float* pj = C + (j0 - 4) * ldc + j0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float lr = pr[u * ldc];
+                const float4 lj = *reinterpret_cast<const float4*>(pj + u * ldc);
+                a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
+            }
+        }
+        const float b00 = __shfl_sync(FULL, a0, j0);
+        const float b10 = __shfl_sync(FULL, a0, j0 + 1), b11 = __shfl_sync(FULL, a1, j0 + 1);
+        const float b20 = __shfl_sync(FULL, a0, j0 + 2), b21 = __shfl_sync(FULL, a1, j0 + 2), b22 = __shfl_sync(FULL, a2, j0 + 2);
+        const float b30 = __shfl_sync(FULL, a0, j0 + 3), b31 = __shfl_sync(FULL, a1, j0 + 3), b32 = __shfl_sync(FULL, a2, j0 + 3), b33 = __shfl_sync(FULL, a3, j0 + 3);
+        const float d0 = sqrtf(b00), r0 = 1.0f / d0;
+        const float l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
+        const float d1 = sqrtf(fmaf(-l10, l10, b11)), r1 = 1.0f / d1;
+        const float l21 = fmaf(-l20, l10, b21) * r1, l31 = fmaf(-l30, l10, b31) * r1;
+        const float d2 = sqrtf(fmaf(-l21, l21, fmaf(-l20, l20, b22))), r2 = 1.0f / d2;
+        const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b32)) * r2;
+        const float d3 = sqrtf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33)))), r3 = 1.0f / d3;
+        float e0 = a0 * r0;
+        a1 = fmaf(-e0, l10, a1); float e1 = a1 * r1;
+        a2 = fmaf(-e1, l21, fmaf(-e0, l20, a2)); float e2 = a2 * r2;
+        a3 = fmaf(-e2, l32, fmaf(-e1, l31, fmaf(-e0, l30, a3))); float e3 = a3 * r3;
+        if (lane == j0) e0 = d0;
+        if (lane == j0 + 1) e1 = d1;
+        if (lane == j0 + 2) e2 = d2;
+        if (lane == j0 + 3) e3 = d3;
+        if (lane < d) {
+            float4 z = av;
+            if (j0 + 0 < lane) z.x = 0.0f;
+            if (j0 + 1 < lane) z.y = 0.0f;
+            if (j0 + 2 < lane) z.z = 0.0f;
+            if (j0 + 3 < lane) z.w = 0.0f;
+            if (lane >= j0) *reinterpret_cast<float4*>(rowp + j0) = z;
+        }
+        __syncwarp();
+        if (lane < d) {
+            if (lane >= j0 + 0) C[(j0 + 0) * ldc + lane] = e0;
+            if (lane >= j0 + 1 && j0 + 1 < d) C[(j0 + 1) * ldc + lane] = e1;
+            if (lane >= j0 + 2 && j0 + 2 < d) C[(j0 + 2) * ldc + lane] = e2;
+            if (lane >= j0 + 3 && j0 + 3 < d) C[(j0 + 3) * ldc + lane] = e3;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (p + 2 < NG) { if ((p & 1) == 0) icl_bar_arrive64<3>(); else icl_bar_arrive64<4>(); }     // panel p is in place: warp 1 may start the sums of panel p + 2
+    }
+}
+
 template <int NR>
 __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
@@ -841,6 +966,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
     float* ecost = sm + L.ecost; float* eb = sm + L.ebetas; int* ei = (int*)(sm + L.eidxs);
     int* tis = (int*)(sm + L.total); float* rsum = sm + L.total + al4(S);        // per-sample reduced sets (packed) and row sums, behind the shared layout
     float* zs = rsum + al4(S * NR);                                              // this iteration's resampling normals [column][row], staged while warp 0 factors
+    float* psum = zs + al4(d * (S - ne));                                        // look-ahead partial sums of the two-warp Cholesky, [2][32][4]
     {   // distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
         float* F = th;
         const float* Fg = ra.feat + (size_t)g * nm * 2 * NV;
@@ -919,11 +1045,11 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
         __syncthreads();
         if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
         __syncthreads();
-        if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
-        else {                                            // the other 15 warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
+        if (warp < 2) icl_chol_lookahead<d>(C, psum, warp, lane);
+        else {                                            // the other 14 warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
             const float* zg = c.zb_iterT + (size_t)it * d * (S - ne);
 #pragma unroll 1
-            for (int i = tid - 32; i < d * (S - ne); i += nt - 32) zs[i] = __ldg(zg + i);
+            for (int i = tid - 64; i < d * (S - ne); i += nt - 64) zs[i] = __ldg(zg + i);
         }
         __syncthreads();
         {   // resample: task = (new row r, group of four columns g4); columns 4 g4 .. 4 g4 + 3 take k = 0 .. 4 g4 + 3 ascending (icf_mvn_row_unrolled's order)
