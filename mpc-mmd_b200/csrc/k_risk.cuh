@@ -57,34 +57,25 @@ __device__ __forceinline__ void bicycle_step(const DCfg& c, float a, float ts, f
 // rollout of a mother sample of mmd_opt: the 22 ridge-fit features (cem_helper.py:553-564, folded: feature_k = sum_t Wfit[k][t] * x[t],
 // ascending t -- the contract's order) are accumulated while the state advances; the 22 independent fma chains fill the issue slots the
 // serial sqrt -> tan -> sincos chain leaves empty.  Positions are written only for the kernels that still read them back (WRITE).
-// MODE 0: features only; 1: also write the positions (kernels that read the mother rollouts back); 2: also fold the rollout's obstacle / lane maxima
-// (latency regime: k_opt_risk then picks the chosen rollouts' maxima instead of re-rolling them -- same values, the maxima are order independent)
+// MODE 0: features only; 1: also write the positions (kernels that read the mother rollouts back).  The latency regime does not come here: k_rollouts<ROLL_OPT>
+// splits the rollout into its bare recurrence and parallel feature / maxima passes there.
 template <int MODE>
 __device__ __forceinline__ void rollout_fit(const DCfg& c, const float* a, const float* s, const float* st0, const float* __restrict__ W /* (11,np) */,
-                                            float* __restrict__ xg, float* __restrict__ yg, float* __restrict__ feat,
-                                            const float* __restrict__ xo = nullptr, const float* __restrict__ yo = nullptr, float* __restrict__ mr = nullptr) {
+                                            float* __restrict__ xg, float* __restrict__ yg, float* __restrict__ feat) {
     float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
     float fx[NV], fy[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) { fx[k] = 0.0f; fy[k] = 0.0f; }
-    float m = 0.0f, l = 0.0f, u = 0.0f;
     const int np = c.np;
 #pragma unroll 1
     for (int t = 0; t < np; t++) {          // the state BEFORE step t is the recorded point  [cem_helper.py:451-458]
         if (MODE == 1) { xg[t] = x; yg[t] = y; }
 #pragma unroll
         for (int k = 0; k < NV; k++) { const float w = W[k * np + t]; fx[k] = fmaf(w, x, fx[k]); fy[k] = fmaf(w, y, fy[k]); }
-        if (MODE == 2) {
-#pragma unroll 4
-            for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
-            l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
-            u = dm::nmax_(u, dm::max0_(y - c.y_ub));
-        }
         bicycle_step(c, a[t], s[t], x, y, vx, vy, psi);          // s = tan(steer), see k_rollouts
     }
 #pragma unroll
     for (int k = 0; k < NV; k++) { feat[k] = fx[k]; feat[NV + k] = fy[k]; }
-    if (MODE == 2) { mr[0] = m; mr[1] = l; mr[2] = u; }
 }
 // Laplace-kernel MMD of nr scalar costs against the zero cost  [kernel_computation.py:67-87]
 __device__ __noinline__ float mmd_cost(const DCfg& c, const float* beta, const float* cost, float sigma) {
@@ -187,8 +178,8 @@ struct RollArgs {
 };
 // mmd_opt: noisy controls of the CTA's samples (2 x nr x np each) + the ridge-fit matrix; the other costs: 4 slots of per-rollout values
 __host__ __device__ inline int roll_tail_floats(int nr) { return nr <= 16 ? 16 : ((nr + 3) & ~3); }
-__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R, int stage_ctrl = 0) {
-    return R == nr ? spb * (4 * roll_tail_floats(nr) + (stage_ctrl ? 2 * nr * np : 0)) : spb * 2 * nr * np + ((NV * np + 3) & ~3);
+__host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R, int stage_ctrl = 0, int fold = 0) {
+    return R == nr ? spb * (4 * roll_tail_floats(nr) + (stage_ctrl ? 2 * nr * np : 0)) : spb * 2 * nr * np + ((NV * np + 3) & ~3) + (fold ? spb * R * 2 * np : 0);
 }
 
 // noisy control pair of element el = row * np + t of sample g  [cem_helper.py:405-443 / 470-508]
@@ -304,6 +295,49 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = tn;
         }
         __syncthreads();
+        if (ra.fold_risk) {
+            // ---- latency regime (a handful of samples per SM): the serial part of a mother rollout is reduced to the bare bicycle recurrence -- positions go to
+            //      shared memory -- and everything that only READS the positions runs in parallel afterwards: one thread per (rollout, feature) for the 22
+            //      ridge-fit chains (ascending t: the contract's order), one warp per rollout with a lane per knot for the obstacle / lane maxima.
+            float* pos = sW + ((NV * np + 3) & ~3);                 // [ns][R][2][np]
+#pragma unroll 1
+            for (int i = tid; i < ns * R; i += nt) {
+                const int ls = i / R, m = i % R, e = (g0 + ls) / a.B;
+                const float* an = sm + ls * 2 * n + (m / nr) * np; const float* sn = sm + ls * 2 * n + n + (m % nr) * np;
+                float* px = pos + (size_t)i * 2 * np; float* py = px + np;
+                const float* st0 = a.state0 + e * 5;
+                float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
+#pragma unroll 1
+                for (int t = 0; t < np; t++) { px[t] = x; py[t] = y; bicycle_step(c, an[t], sn[t], x, y, vx, vy, psi); }
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int task = tid; task < ns * R * 2 * NV; task += nt) {
+                const int i = task / (2 * NV), kk = task % (2 * NV), k = kk < NV ? kk : kk - NV;
+                const float* p = pos + (size_t)i * 2 * np + (kk < NV ? 0 : np); const float* w = sW + k * np;
+                float f = 0.0f;
+#pragma unroll 5
+                for (int t = 0; t < np; t++) f = fmaf(w[t], p[t], f);
+                ra.feat[((size_t)g0 * R + i) * 2 * NV + kk] = f;
+            }
+#pragma unroll 1
+            for (int i = warp; i < ns * R; i += nt / 32) {
+                const int ls = i / R, e = (g0 + ls) / a.B;
+                const float* px = pos + (size_t)i * 2 * np; const float* py = px + np;
+                const float* xo = a.x_obs + (size_t)e * c.O * T_; const float* yo = a.y_obs + (size_t)e * c.O * T_;
+                float m = 0.0f, l = 0.0f, u = 0.0f;
+                for (int t = lane; t < np; t += 32) {
+                    const float x = px[t], y = py[t];
+#pragma unroll 4
+                    for (int o = 0; o < c.O; o++) m = dm::nmax_(m, fbar(c, x, y, xo[o * T_ + t], yo[o * T_ + t]));
+                    l = dm::nmax_(l, dm::max0_(-y + c.y_lb));
+                    u = dm::nmax_(u, dm::max0_(y - c.y_ub));
+                }
+                m = warp_nmax(m); l = warp_nmax(l); u = warp_nmax(u);
+                if (lane == 0) { float* mr = ra.mrisk + ((size_t)g0 * R + i) * 3; mr[0] = m; mr[1] = l; mr[2] = u; }
+            }
+            return;
+        }
         // mother sample m = i*nr + j uses acc noise i, steer noise j  [cem_helper.py:510-511]
 #pragma unroll 1
         for (int i = tid; i < ns * R; i += nt) {
@@ -311,8 +345,6 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             const float* an = sm + ls * 2 * n + (m / nr) * np; const float* sn = sm + ls * 2 * n + n + (m % nr) * np;
             float* ft = ra.feat + ((size_t)g * R + m) * 2 * NV;
             if (ra.write_rolls) rollout_fit<1>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
-            else if (ra.fold_risk) rollout_fit<2>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft, a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_,
-                                                  ra.mrisk + ((size_t)g * R + m) * 3);
             else rollout_fit<0>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft);
         }
     } else {

@@ -158,9 +158,9 @@ static int roll_spb(const mpcmmd_handle_s* h, int kind, int n_samples) {
     while (spb > 1 && (n_samples + spb - 1) / spb < 4 * h->sm_count) spb--;
     return spb;
 }
-static size_t roll_smem_for(const DCfg& d, int kind, int spb, int stage) {
+static size_t roll_smem_for(const DCfg& d, int kind, int spb, int stage, int fold = 0) {
     const int R = (kind == MPCMMD_COST_MMD_OPT) ? d.nm : d.nr;
-    return (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage) * sizeof(float);
+    return (size_t)roll_smem_floats(spb, d.nr, d.np, R, stage, fold) * sizeof(float);
 }
 // largest dynamic shared memory any launch of this handle can ask for (opt-in at create)
 static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
@@ -168,6 +168,7 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     const size_t a = roll_smem_for(d, kind, roll_spb(h, kind, 1 << 30), 0), b = roll_smem_for(d, kind, roll_spb(h, kind, 1), roll_stage_ctrl(h, kind, 1));
     size_t c = 0;
     for (int spb = 1; spb <= 8; spb++) { const size_t v = roll_smem_for(d, kind, spb, kind != MPCMMD_COST_MMD_OPT); if (v <= 96 * 1024 && v > c) c = v; }
+    if (kind == MPCMMD_COST_MMD_OPT) { const size_t v = roll_smem_for(d, kind, 1, 0, 1); if (v > c) c = v; }      // latency regime: positions of one sample's mother rollouts
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
@@ -518,7 +519,8 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         }
     }
     {
-        const int grid = (r.n_samples + ra.spb - 1) / ra.spb; const size_t rsm = roll_smem_for(d, r.cost_kind, ra.spb, ra.stage_ctrl);
+        if (ra.fold_risk) ra.spb = 1;
+        const int grid = (r.n_samples + ra.spb - 1) / ra.spb; const size_t rsm = roll_smem_for(d, r.cost_kind, ra.spb, ra.stage_ctrl, ra.fold_risk);
         if (opt) k_rollouts<ROLL_OPT><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
         else if (ra.stage_ctrl) k_rollouts<ROLL_STAGED><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
         else k_rollouts<ROLL_FLY><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
