@@ -511,6 +511,7 @@ __device__ __forceinline__ void icf_mvn_row_regs(const float* __restrict__ LT, i
     }
 }
 
+template <int d> __device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float* __restrict__ ps, int warp, int lane);
 // LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): no register cap (156 instead of the 56 registers
 // that let 12 chains share an SM) and the resampling normals prefetched behind the Cholesky (mmd_opt p50 at batch 1: 8.3 -> 7.4 ms)
 // FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
@@ -617,8 +618,14 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
                 for (int k = 0; k < d; k++) zpre[k] = __ldg(zp + k * (S - ne));
             }
         }
-        // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel)
+        // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel).  The two-warp look-ahead variant of the
+        //    latency kernel (icl_chol_lookahead, partial sums in the dead row region) was measured here too (-DICF_CHOL_LOOKAHEAD): 155.7 vs 153.6 ms per 200-episode
+        //    solve -- under the 56-register cap it spills, and with 12 chains per SM the phase is bound by issued instructions, not by warp 0's critical path.
+#ifdef ICF_CHOL_LOOKAHEAD
+        if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane);
+#else
         if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
+#endif
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
         //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in
