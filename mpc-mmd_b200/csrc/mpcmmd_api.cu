@@ -168,7 +168,7 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     const size_t a = roll_smem_for(d, kind, roll_spb(h, kind, 1 << 30), 0), b = roll_smem_for(d, kind, roll_spb(h, kind, 1), roll_stage_ctrl(h, kind, 1));
     size_t c = 0;
     for (int spb = 1; spb <= 8; spb++) { const size_t v = roll_smem_for(d, kind, spb, kind != MPCMMD_COST_MMD_OPT); if (v <= 96 * 1024 && v > c) c = v; }
-    if (kind == MPCMMD_COST_MMD_OPT) { const size_t v = roll_smem_for(d, kind, 1, 0, 1); if (v > c) c = v; }      // latency regime: positions of one sample's mother rollouts
+    if (kind == MPCMMD_COST_MMD_OPT && inner_cem_is_fast(d)) { const size_t v = roll_smem_for(d, kind, 1, 0, 1); if (v > c) c = v; }      // latency regime (num_reduced <= 5 only): positions of one sample's mother rollouts
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
