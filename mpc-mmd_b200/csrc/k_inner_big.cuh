@@ -172,13 +172,58 @@ __global__ void __launch_bounds__(NT) k_inner_cem_big(DCfg c, RollArgs ra, float
         __syncthreads();
         // block-wide Cholesky, left-looking by panels of four columns, rows strided over the threads; entry (r, j) accumulates fma(-L_rk, L_jk, .) for k ascending,
         // then the pivot's sqrt / reciprocal scaling (the contract's order).  The factor is kept transposed in the upper triangle: LT[k][q] = L[q][k].
+        // Two levels: at the start of every SUPER-PANEL of 16 columns one pass brings all 16 columns of every row up to date with the finished columns k < J0
+        // (16 accumulators per row in registers: one load of L[r][k] feeds 16 fmas, the (nm+1)^2 factor streams from L2 once per 16 columns instead of once per 4);
+        // the four 4-column panels inside then only add the columns k >= J0 of their own super-panel.  Per entry the k order stays ascending.
         for (int p = 0; p < (d + 3) / 4; p++) {
-            const int j0 = 4 * p;
+            const int j0 = 4 * p, J0 = j0 & ~15;
+            if (j0 == J0 && J0 > 0) {
+                for (int r = J0 + tid; r < d; r += nt) {
+                    float acc[16];
+                    float* crow = C + (size_t)r * ldc + J0;             // ldc is a multiple of 4 and J0 of 16: float4 accesses; columns beyond d stay inside the padded row only
+                    const int nq = min(16, ldc - J0);                   // for the last, partial super-panel
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) {
+                        if (u < nq) { const float4 v = *reinterpret_cast<const float4*>(crow + u); acc[u] = v.x; acc[u + 1] = v.y; acc[u + 2] = v.z; acc[u + 3] = v.w; }
+                        else { acc[u] = 0.0f; acc[u + 1] = 0.0f; acc[u + 2] = 0.0f; acc[u + 3] = 0.0f; }
+                    }
+                    // L[r][k] is the one load per step that is private to the thread (L2 / HBM latency); the 16 column operands are the same for every thread
+                    // (L1 hits).  J0 is a multiple of 16: the private loads are fetched eight steps ahead, double buffered.
+                    const float* pr = C + r;
+                    float cur[8], nxt[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cur[q] = pr[(size_t)q * ldc];
+                    for (int k0 = 0; k0 < J0; k0 += 8) {
+                        if (k0 + 8 < J0) {
+#pragma unroll
+                            for (int q = 0; q < 8; q++) nxt[q] = pr[(size_t)(k0 + 8 + q) * ldc];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float lr = -cur[q];
+                            const float* lrow = C + (size_t)(k0 + q) * ldc + J0;
+#pragma unroll
+                            for (int u = 0; u < 16; u += 4) {
+                                if (u < nq) {
+                                    const float4 l = *reinterpret_cast<const float4*>(lrow + u);
+                                    acc[u] = fmaf(lr, l.x, acc[u]); acc[u + 1] = fmaf(lr, l.y, acc[u + 1]); acc[u + 2] = fmaf(lr, l.z, acc[u + 2]); acc[u + 3] = fmaf(lr, l.w, acc[u + 3]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4)
+                        if (u < nq) *reinterpret_cast<float4*>(crow + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+                }
+                __syncthreads();
+            }
             // every thread first finishes the partial sums of its rows, rows j0..j0+3 publish the diagonal block
             for (int r = j0 + tid; r < d; r += nt) {
                 const float4 av = *reinterpret_cast<const float4*>(C + (size_t)r * ldc + j0);
                 float a0 = av.x, a1 = av.y, a2 = av.z, a3 = av.w;
-                for (int k = 0; k < j0; k++) {
+                for (int k = J0; k < j0; k++) {
                     const float lr = C[(size_t)k * ldc + r];
                     const float4 lj = *reinterpret_cast<const float4*>(C + (size_t)k * ldc + j0);
                     a0 = fmaf(-lr, lj.x, a0); a1 = fmaf(-lr, lj.y, a1); a2 = fmaf(-lr, lj.z, a2); a3 = fmaf(-lr, lj.w, a3);
