@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 // row => same arithmetic => same bits), so 96 threads are ~93 % busy in the sample stage and in the row-per-thread
 // resampling stage.
 #define RISKO_THREADS 96
-#define RISKO_THREADS_BIG 256  // num_reduced^2 + 1 > 32: one CTA per SM (100+ KB of shared memory), so the CTA itself has to fill the SM
-__host__ __device__ constexpr int risko_threads(int nr) { return nr * nr + 1 <= 32 ? RISKO_THREADS : RISKO_THREADS_BIG; }
+#define RISKO_THREADS_BIG 512  // num_reduced^2 + 1 > 32: one CTA per SM (100+ KB of shared memory), so the CTA itself has to fill the SM
+// measured per solve at 8 episodes (tools/time_generic_nr.py), 256 / 512 threads: num_reduced 6: 4.0 / 6.5 ms, 8: 13.4 / 11.9 ms, 10: 24.2 / 21.5 ms
+__host__ __device__ constexpr int risko_threads(int nr) { return nr * nr + 1 <= 32 ? RISKO_THREADS : (nr <= 7 ? 256 : RISKO_THREADS_BIG); }
 
 struct OptLayout {          // shared-memory carve-up (in floats); every offset is a multiple of 4 floats (16 B)
     int F, D, small, red, th, cost, betas, idxs, key64, perm, C, rd, mean, eth, xc, ecost, ebetas, eidxs, rs;
