@@ -37,6 +37,7 @@ CEM_KW = {}
 WORKLOAD_NAME = ("configs[1]: synthetic_static_obs, cvar + mmd_opt, beta noise 0.3, num_obs 4, num_prime 50, num_reduced 5, "
                  "200-episode sweep (400 solves/step)")
 METRIC = "MPC solves/sec"
+CONCURRENT_MIN_SAMPLES = 7500          # CEM samples per launch (episodes x num_batch) from which the cost functions of a step solve concurrently on two streams
 
 # The default (and the driver's) workload is configs[1].  The other BASELINE configs are parity-test cases (tests/); `--workload` lets
 # them be timed with the same harness for the numbers quoted in DESIGN.md / profiles/ -- those lines are not the headline.
@@ -254,6 +255,10 @@ def main():
             self.prob = self.probs[COSTS[-1]]
             self.streams = {c: torch.cuda.Stream(dev) for c in COSTS}
             self.pool = ThreadPoolExecutor(max_workers=len(COSTS))
+            # ... when every launch fills the device.  A shard of a few waves of chains (25 / 50 episodes per rank: the 8- / 4-GPU sweep) gains nothing from two
+            # concurrent graphs -- the short latency-bound kernels of cvar and the chain waves of mmd_opt only delay each other (tools/overlap_probe.py: 25 episodes
+            # 24.8 ms concurrent, 24.4 ms back to back; 50: 45.8 / 44.6; 100: 84.9 / 86.7) -- so small shards solve their cost functions back to back on one stream
+            self.concurrent = len(COSTS) > 1 and self.E * self.probs[COSTS[0]].num_batch >= CONCURRENT_MIN_SAMPLES
             self.host = scenes.static_batch(self.prob, self.eps, VARIANT)
             self.dev_in = {k: torch.as_tensor(self.host[k], device=dev) for k in keys}
             self.pinned_np = {k: torch.as_tensor(self.host[k]).pin_memory().numpy() for k in keys}
@@ -286,6 +291,10 @@ def main():
         def step_device(self):
             cur = torch.cuda.current_stream(dev)
             outs = {}
+            if not self.concurrent:
+                for cost in COSTS:
+                    outs[cost] = self.probs[cost].solve_batch_device(cost, *[self.dev_in[k] for k in keys])
+                return self.record(outs)
             for cost in COSTS:
                 st = self.streams[cost]
                 st.wait_stream(cur)
@@ -297,6 +306,8 @@ def main():
 
         def step_host(self):
             """host buffers in, host buffers out: one synchronous C-ABI call per cost function, issued from one host thread each"""
+            if not self.concurrent:
+                return {cost: self.probs[cost].solve_batch(cost, *[self.pinned_np[k] for k in keys]) for cost in COSTS}
             futs = {cost: self.pool.submit(self.probs[cost].solve_batch, cost, *[self.pinned_np[k] for k in keys]) for cost in COSTS}
             return {cost: f.result() for cost, f in futs.items()}
 
@@ -331,6 +342,7 @@ def main():
     # ---- device-resident throughput (`value`) on the headline workload
     arm = Arm(args.scaling)
     prob, E = arm.prob, arm.E
+    concurrent_flag = arm.concurrent
     HEAVY = COSTS[-1]                                                             # the cost whose risk stage the roofline describes
     with ClockSampler(local) as clk:
         ms_total, t_wall, recs, launches_per_step = arm.time_device(K, W)
@@ -458,7 +470,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": line_config(args.scaling),
-                "details": {"episodes_this_rank": E, "projection": args.projection, "concurrency": "one handle + CUDA stream per cost function (cvar and mmd_opt solve concurrently)", "l2": "flushed between timed steps (256 MiB fill)",
+                "details": {"episodes_this_rank": E, "projection": args.projection, "concurrency": ("one handle + CUDA stream per cost function (cvar and mmd_opt solve concurrently)" if concurrent_flag else "one handle per cost function, solved back to back on one stream (shard too small for concurrent graphs to pay)"), "l2": "flushed between timed steps (256 MiB fill)",
                             "parallelism": "episodes sharded %d-way, no data-path collective" % world, "accepted": accepted, "wall_s_timed_region": t_wall},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "matches_device_path": bool(same)},
                 "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu, "latency_1gpu_batch1": lat,

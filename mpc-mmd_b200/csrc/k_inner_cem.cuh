@@ -45,6 +45,11 @@ __device__ __forceinline__ f2 exp2_nonpos(float xa, float xb) {
     const float sca = dm::u2f((dm::f2u(ta) << 23) + 0x3f800000u), scb = dm::u2f((dm::f2u(tb) << 23) + 0x3f800000u);
     return mul2(y, pack(sca, scb));
 }
+// 16-byte shared-memory load from a 32-bit shared-window address (volatile: stays inside its loop trip, in program order with the barriers around the phase)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
 // MUFU.EX2 (opt-in fast-math mode only, MPCMMD_MATH=fast): 2^x to ~2^-22 relative, not reproducible on the CPU oracle
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 }  // namespace pk
@@ -58,20 +63,28 @@ __device__ __forceinline__ pk::f2 lap2(float da, float db, pk::f2 sc2) {
     else return pk::exp2_nonpos(-pk::lo(d), -pk::hi(d));
 }
 
+// the same from already scaled arguments xa = da * sc, xb = db * sc (each the rounded product lap2 forms)
+template <bool FM>
+__device__ __forceinline__ pk::f2 lap2s(float xa, float xb) {
+    if constexpr (FM) return pk::pack(pk::ex2_approx(xa), pk::ex2_approx(xb));
+    else return pk::exp2_nonpos(-xa, -xb);
+}
+
 #define ICF_THREADS 96
 #define ICF_MAX_S 128       // candidates per inner iteration handled by the one-warp selection (4 per lane)
 #define ICF_MAX_NE 12       // elites (covariance operands are read as 3 float4 per column)
 
 struct FastLayout {         // shared-memory carve-up in floats; every offset is a multiple of 4 floats
     int D, th, cost, betas, idxs, eth, ecost, ebetas, eidxs, perm, xc, C, mean, small, red, total;
-    int ldt, ldc;
+    int ldt, ldc, ldd;
 };
 __host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
     FastLayout L; const int nm = nr * nr, d = nm + 1;
     L.ldt = d | 1;                           // odd row stride: thread-per-row accesses are bank-conflict free
     L.ldc = al4(d);
+    L.ldd = al4(nm);                         // distance-table row stride: rows start 16-byte aligned, so the row-sum loop reads four columns per LDS.128
     int q = 0;
-    L.D = q; q += al4(nm * nm);
+    L.D = q; q += nm * L.ldd;
     {   // the S - ne resampled rows (iteration 0 reads the constant theta0 table straight from global memory); the region is also borrowed by the
         // mother features while D is built and by the centered elites xc between the elite gather and the covariance (the rows are dead then)
         int n = (S - ne) * L.ldt;
@@ -118,10 +131,13 @@ __device__ __noinline__ int top_abs_exact(const float* __restrict__ row) {     /
 
 // the QP + MMD cost of one beta sample given its reduced set (indices ti, ascending |theta|) and bandwidth sigma
 // [compute_beta.py:70-91, 120-129]; bit-identical to the second half of beta_sample<NR> of k_risk.cuh
-template <int NR, bool FM = false>
+// LDD = row stride of D in floats; a multiple of four selects the vectorised row-sum loop (four columns per 16-byte load, same operations in the same order)
+template <int NR, bool FM = false, int LDD = NR * NR>
 __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], float sigma, const float* __restrict__ D,
                                            float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
     constexpr int nm = NR * NR;
+    constexpr bool VEC = (LDD % 4 == 0) && nm >= 4;
+    constexpr int MV = VEC ? (nm & ~3) : 0;          // columns handled by the vectorised loop
     const float rinv = 1.0f / sigma;
     const float sc = FM ? -rinv * 1.44269504088896341f : rinv;
     const pk::f2 rinv2 = pk::dup(sc);
@@ -133,9 +149,36 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
     for (int p = 0; p < NP; p++) rs2[p] = pk::dup(0.0f);
     const float* Dr[NR];
 #pragma unroll
-    for (int i = 0; i < NR; i++) Dr[i] = D + ti[i] * nm;        // D is symmetric bit for bit: row idx_i
+    for (int i = 0; i < NR; i++) Dr[i] = D + ti[i] * LDD;       // D is symmetric bit for bit: row idx_i
+    if constexpr (VEC) {
+        // The scaling d * (1/sigma) runs on the register pairs the 16-byte loads deliver (columns m, m+1 of ONE row); the clamp of the exponential's argument is a
+        // scalar instruction whose destination is free, so it drops each value into the (row 2p, row 2p+1) pair the packed polynomial works on -- no register moves.
+        // Addresses: one loop-carried register (table base + 4 m) and one multiply-add per row and trip, instead of an index and a scaled add per row.
+        uint32_t dm = pk::smem_addr(D);
 #pragma unroll 1
-    for (int m = 0; m + 1 < nm; m += 2) {
+        for (int m = 0; m < MV; m += 4, dm += 16) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float4 va = pk::lds128(dm + (uint32_t)ti[2 * p] * (LDD * 4)), vb = pk::lds128(dm + (uint32_t)ti[2 * p + 1] * (LDD * 4));
+                float ax, ay, az, aw, bx, by, bz, bw;
+                pk::unpack(pk::mul2(pk::pack(va.x, va.y), rinv2), ax, ay); pk::unpack(pk::mul2(pk::pack(va.z, va.w), rinv2), az, aw);
+                pk::unpack(pk::mul2(pk::pack(vb.x, vb.y), rinv2), bx, by); pk::unpack(pk::mul2(pk::pack(vb.z, vb.w), rinv2), bz, bw);
+                rs2[p] = pk::add2(rs2[p], lap2s<FM>(ax, bx));
+                rs2[p] = pk::add2(rs2[p], lap2s<FM>(ay, by));
+                rs2[p] = pk::add2(rs2[p], lap2s<FM>(az, bz));
+                rs2[p] = pk::add2(rs2[p], lap2s<FM>(aw, bw));
+            }
+            if constexpr (NR & 1) {
+                const float4 vc = pk::lds128(dm + (uint32_t)ti[NR - 1] * (LDD * 4));
+                pk::f2 e = lap2<FM>(vc.x, vc.y, rinv2);
+                rsl = rsl + pk::lo(e); rsl = rsl + pk::hi(e);
+                e = lap2<FM>(vc.z, vc.w, rinv2);
+                rsl = rsl + pk::lo(e); rsl = rsl + pk::hi(e);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int m = MV; m + 1 < nm; m += 2) {
 #pragma unroll
         for (int p = 0; p < NP; p++) {
             rs2[p] = pk::add2(rs2[p], lap2<FM>(Dr[2 * p][m], Dr[2 * p + 1][m], rinv2));
@@ -239,7 +282,7 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
 }
 
 // one beta sample of the inner CEM [compute_beta.py:113-129, 70-91]; bit-identical to beta_sample<NR> of k_risk.cuh
-template <int NR, bool FM = false>
+template <int NR, bool FM = false, int LDD = NR * NR>
 __device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __restrict__ row, const float* __restrict__ D,
                                                   float* __restrict__ beta_out, int* __restrict__ idx_out /* one packed word */) {
     constexpr int nm = NR * NR;
@@ -266,7 +309,7 @@ __device__ __forceinline__ float beta_sample_fast(const DCfg& c, const float* __
 #pragma unroll
         for (int p = 0; p < NR; p++) ti[p] = (pkd >> (5 * p)) & 31;
     }
-    return beta_eval<NR, FM>(c, ti, row[nm], D, beta_out, idx_out);
+    return beta_eval<NR, FM, LDD>(c, ti, row[nm], D, beta_out, idx_out);
 }
 
 // float -> uint32 whose unsigned order is "ascending float, -0 == +0, NaN last" (jnp.argsort order of the costs)
@@ -515,17 +558,19 @@ template <int d> __device__ __forceinline__ void icl_chol_lookahead(float* __res
 // LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): no register cap (156 instead of the 56 registers
 // that let 12 chains share an SM) and the resampling normals prefetched behind the Cholesky (mmd_opt p50 at batch 1: 8.3 -> 7.4 ms)
 // FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
-template <int NR, bool LAT, bool FM = false>
+// SC / NEC = compile-time copies of the inner CEM's sample / elite counts (0 = read them from the configuration): with the reference's sizes (100 / 11) baked in, the
+// whole shared-memory layout folds into immediate offsets, which takes the address arithmetic the 56-register cap otherwise re-derives in every phase out of the kernel
+template <int NR, bool LAT, bool FM = false, int SC = 0, int NEC = 0>
 __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;
-    constexpr int nm = NR * NR, d = nm + 1;
+    constexpr int nm = NR * NR, d = nm + 1, LDD = (nm + 3) & ~3;       // = FastLayout::ldd
     static_assert(d <= 32, "one covariance row per lane");
     constexpr int NPAIR = (d + 1) / 2;               // packed column pairs of a covariance / Cholesky row
     const int tid = threadIdx.x, nt = ICF_THREADS, warp = tid >> 5, lane = tid & 31;
-    const int S = c.S_in, ne = c.n_el_in;
+    const int S = SC ? SC : c.S_in, ne = NEC ? NEC : c.n_el_in;
     const FastLayout L = fast_layout(NR, S, ne);
     const int ldt = L.ldt, ldc = L.ldc;
     float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = ra.bscratch + (size_t)g * S * (NR + 1); int* idxs = (int*)(betas + S * NR);
@@ -546,7 +591,7 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
             float dist = 0.0f;
 #pragma unroll 2
             for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
-            D[i] = dist;
+            D[(i / nm) * LDD + i % nm] = dist;
         }
         __syncthreads();
     }
@@ -569,7 +614,7 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;      // where this iteration's new rows live
         // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
 #pragma unroll 1
-        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR, FM>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
+        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR, FM, LDD>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
         if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);
@@ -772,7 +817,7 @@ __device__ __forceinline__ float icl_rowsum(const float* __restrict__ Drow, floa
     return rs;
 }
 // reduced kernel, KKT solve and cost of one beta sample from its row sums: second half of beta_eval, operation for operation
-template <int NR>
+template <int NR, int LDD = NR * NR>
 __device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sigma, const float* __restrict__ rowsum, const float* __restrict__ D,
                                             float* __restrict__ beta_out) {
     constexpr int nm = NR * NR;
@@ -790,7 +835,7 @@ __device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sig
         for (int i = 0; i < NR; i++) {
             K[i][i] = 1.0f;
 #pragma unroll
-            for (int j = 0; j < i; j++) dv[e++] = D[ti[i] * nm + ti[j]];
+            for (int j = 0; j < i; j++) dv[e++] = D[ti[i] * LDD + ti[j]];
         }
         dv[NE] = dv[NE - 1];
         float ev[NE + 1];
@@ -961,7 +1006,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
     const RiskArgs& a = ra.r;
     const int g = blockIdx.x;
     if (g >= a.n_samples) return;
-    constexpr int nm = NR * NR, d = nm + 1, NG = (d + 3) / 4;
+    constexpr int nm = NR * NR, d = nm + 1, NG = (d + 3) / 4, LDD = (nm + 3) & ~3;       // = FastLayout::ldd
     const int tid = threadIdx.x, nt = ICL_THREADS, warp = tid >> 5, lane = tid & 31;
     const int S = c.S_in, ne = c.n_el_in;
     const FastLayout L = fast_layout(NR, S, ne);
@@ -986,7 +1031,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
             float dist = 0.0f;
 #pragma unroll 2
             for (int f = 0; f < 2 * NV; f++) dist = dist + fabsf(Fa[f] - Fb[f]);
-            D[i] = dist;
+            D[(i / nm) * LDD + i % nm] = dist;
         }
         __syncthreads();
     }
@@ -1012,12 +1057,12 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
         for (int task = tid; task < n_new * NR; task += nt) {
             const int s = task / NR, i = task - s * NR;
             const float rinv = 1.0f / rows[s * rstride + nm];
-            rsum[task] = icl_rowsum<NR>(D + ((tis[s] >> (5 * i)) & 31) * nm, rinv);
+            rsum[task] = icl_rowsum<NR>(D + ((tis[s] >> (5 * i)) & 31) * LDD, rinv);
         }
         __syncthreads();
 #pragma unroll 1
         for (int s = tid; s < n_new; s += nt) {
-            cost[s] = icl_finish<NR>(c, tis[s], rows[s * rstride + nm], rsum + s * NR, D, betas + s * NR);
+            cost[s] = icl_finish<NR, LDD>(c, tis[s], rows[s * rstride + nm], rsum + s * NR, D, betas + s * NR);
             idxs[s] = tis[s];
         }
         __syncthreads();

@@ -44,6 +44,7 @@ static int raise_smem(int device, const void* fn, size_t bytes, bool carveout_ma
 }
 extern "C" int mpcmmd_version(void) { return 100; }
 
+#define MAX_GROUPS 4
 struct mpcmmd_handle_s {
     int device = 0;
     mpcmmd_config cfg;         // host copy (matrix pointers are NOT valid after create)
@@ -74,9 +75,10 @@ struct mpcmmd_handle_s {
     std::map<std::pair<int, int>, int> graph_launches;
     int last_launches = 0;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;       // second branch of a solve graph whose episodes are split into two groups (see solve_groups)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int groups_override = 0;                 // MPCMMD_GROUPS=1|2: force the number of episode groups of a solve graph (0 = automatic)
+    cudaStream_t aux_stream[MAX_GROUPS - 1] = {};   // further branches of a solve graph whose episodes are split into groups (see solve_groups)
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS - 1] = {};
+    int groups_override = 0;                 // MPCMMD_GROUPS=1..4: force the number of episode groups of a solve graph (0 = automatic)
+    int prio_mode = 0;                       // MPCMMD_PRIO=0|1|2 (experiment, default off): highest stream priority on the kernel nodes of mmd_opt graphs (1) / of the other cost functions' graphs (2)
 };
 
 // ---- episode-offset view of a handle's workspace: every per-episode array advanced by e0 episodes.  A solve graph can then enqueue disjoint episode
@@ -204,6 +206,7 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_WARP) switch (d.nr) {
         case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
     }
+    if (kind == INNER_CTA && d.nr == 5 && d.S_in == 100 && d.n_el_in == 11) return k_inner_cem_fast<5, false, false, 100, 11>;      // the reference's sizes as compile-time constants
     if (kind == INNER_CTA) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, false>; case 3: return k_inner_cem_fast<3, false>; case 4: return k_inner_cem_fast<4, false>; case 5: return k_inner_cem_fast<5, false>;
     }
@@ -417,9 +420,22 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
         }
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_GROUPS - 1; i++) {
+        CK(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
     { const char* gv = getenv("MPCMMD_GROUPS"); h->groups_override = gv ? atoi(gv) : 0; }
+    { const char* pv = getenv("MPCMMD_PRIO"); h->prio_mode = pv ? atoi(pv) : 0; }
+    {   // MPCMMD_CARVE=1 (experiment): every kernel of a solve prefers the maximum shared-memory carve-out, so that kernels of concurrent branches / handles
+        // never wait for an SM to drain before its L1 / shared split can change
+        const char* cv = getenv("MPCMMD_CARVE");
+        if (cv) {
+            const void* fns[] = {(const void*)k_project, (const void*)k_rollouts<ROLL_OPT>, (const void*)k_rollouts<ROLL_FLY>, (const void*)k_rollouts<ROLL_STAGED>,
+                                 (const void*)k_opt_risk, (const void*)k_select, (const void*)k_noise, (const void*)k_init, (const void*)k_boundary};
+            for (const void* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv) == 1 ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault);
+        }
+    }
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     return 0;
@@ -431,9 +447,8 @@ extern "C" int mpcmmd_destroy(mpcmmd_handle h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (void* p : h->allocs) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    for (int i = 0; i < MAX_GROUPS - 1; i++) { if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return 0;
 }
@@ -607,13 +622,16 @@ static int enqueue_solve(mpcmmd_handle_s* h, int kind, int n_ep, cudaStream_t s,
     return 0;
 }
 
-// number of episode groups of a solve graph.  Two groups pay off for mmd_opt launches of a few waves of chains (strong-scaled shards: 25 episodes = 2500
-// chains on 1776 resident CTAs): measured 27.8 -> 25.2 ms per cvar + mmd_opt step at 25 episodes, neutral from ~100 episodes on (tools/stream_probe.py)
+// number of episode groups (branches) of a solve graph.  Groups pay off for mmd_opt launches of a few waves of chains (strong-scaled shards: 25 episodes = 2500
+// chains on 1776 resident CTAs): the groups drift out of phase, so one group's tail wave and small kernels are filled by the others' chains.  Measured
+// (tools/overlap_probe.py, mmd_opt solve of 25 / 50 / 100 episodes): 1 group 24.2 / 41.9 / 78.8 ms, 2 groups 22.6 / 41.1 / 79.5, 3 groups 21.6 / 39.9 / 78.2,
+// 4 groups 22.5 / 42.9 / 78.4.
 static int solve_groups(const mpcmmd_handle_s* h, int kind, int n_ep) {
     if (n_ep < 2 || h->inner_mode == INNER_WARP) return 1;         // the warp-per-chain kernel's row stash is per persistent CTA, not per chain
-    if (h->groups_override == 1 || h->groups_override == 2) return h->groups_override;
+    if (h->groups_override >= 1 && h->groups_override <= MAX_GROUPS) return h->groups_override < n_ep ? h->groups_override : n_ep;
     const long long chains = (long long)n_ep * h->d.B;
-    return (kind == MPCMMD_COST_MMD_OPT && inner_cem_is_fast(h->d) && chains > 6LL * h->sm_count && chains <= 36LL * h->sm_count) ? 2 : 1;
+    if (kind != MPCMMD_COST_MMD_OPT || !inner_cem_is_fast(h->d) || chains <= 6LL * h->sm_count || chains > 36LL * h->sm_count) return 1;
+    return chains > 12LL * h->sm_count ? 3 : 2;
 }
 static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
     auto key = std::make_pair(kind, n_ep);
@@ -623,22 +641,46 @@ static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* ou
     int launches = 0;
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    if (solve_groups(h, kind, n_ep) == 2) {
-        // two episode groups on two branches of the graph: the small latency-bound kernels of one group (projection, rollouts, selection) overlap
-        // the reduced-set kernel of the other, and the tail wave of one group's chains is filled by the other group's
-        const int nA = (n_ep + 1) / 2, nB = n_ep - nA;
-        int la = 0, lb = 0;
+    const int G = solve_groups(h, kind, n_ep);
+    if (G > 1) {
+        // G episode groups on G branches of the graph: the small latency-bound kernels of one group (projection, rollouts, selection) overlap
+        // the reduced-set kernel of the others, and the tail wave of one group's chains is filled by the other groups'
         cudaEventRecord(h->ev_fork, h->own_stream);
-        cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0);
-        rc = enqueue_solve(h, kind, nA, h->own_stream, &la);
-        if (!rc) { const ViewSave sv = push_view(h, nA); rc = enqueue_solve(h, kind, nB, h->aux_stream, &lb); pop_view(h, sv); }
-        cudaEventRecord(h->ev_join, h->aux_stream);
-        cudaStreamWaitEvent(h->own_stream, h->ev_join, 0);
-        launches = la + lb;
+        for (int gi = 1; gi < G; gi++) cudaStreamWaitEvent(h->aux_stream[gi - 1], h->ev_fork, 0);
+        for (int gi = 0; gi < G && !rc; gi++) {
+            const int e0 = (int)((long long)gi * n_ep / G), e1 = (int)((long long)(gi + 1) * n_ep / G);
+            int l = 0;
+            const ViewSave sv = push_view(h, e0);
+            rc = enqueue_solve(h, kind, e1 - e0, gi == 0 ? h->own_stream : h->aux_stream[gi - 1], &l);
+            pop_view(h, sv);
+            launches += l;
+        }
+        for (int gi = 1; gi < G; gi++) { cudaEventRecord(h->ev_join[gi - 1], h->aux_stream[gi - 1]); cudaStreamWaitEvent(h->own_stream, h->ev_join[gi - 1], 0); }
     } else rc = enqueue_solve(h, kind, n_ep, h->own_stream, &launches);
     cudaError_t ce = cudaStreamEndCapture(h->own_stream, &g);
     if (rc) { if (ce == cudaSuccess && g) cudaGraphDestroy(g); return -1; }
     CK(ce);
+    if ((h->prio_mode == 1 && kind == MPCMMD_COST_MMD_OPT) || (h->prio_mode == 2 && kind != MPCMMD_COST_MMD_OPT)) {
+        // Experiment (default off; measured, no effect): when the sweep's cost functions solve concurrently on one device, MPCMMD_PRIO=1 gives the kernel nodes
+        // of mmd_opt graphs (the long pole) the device's highest priority, MPCMMD_PRIO=2 those of the short latency-bound cost functions.  The attribute is accepted
+        // on every node, and the cvar + mmd_opt step of 25 / 50 / 100 episodes takes the same time in all three modes (profiles/r02_overlap_probe.md).
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi != lo) {
+            size_t nn = 0; int nset = 0, nfail = 0;
+            if (cudaGraphGetNodes(g, nullptr, &nn) == cudaSuccess && nn) {
+                std::vector<cudaGraphNode_t> nodes(nn);
+                cudaGraphGetNodes(g, nodes.data(), &nn);
+                for (auto nd : nodes) {
+                    cudaGraphNodeType ty;
+                    if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                    cudaKernelNodeAttrValue v; memset(&v, 0, sizeof(v)); v.priority = hi;
+                    if (cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributePriority, &v) == cudaSuccess) nset++; else nfail++;
+                }
+            }
+            cudaGetLastError();
+            if (getenv("MPCMMD_DEBUG")) fprintf(stderr, "[mpcmmd] graph kind %d n_ep %d: priority %d (range %d..%d) set on %d kernel nodes, %d failures\n", kind, n_ep, hi, lo, hi, nset, nfail);
+        }
+    }
     cudaGraphExec_t ge;
     ce = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
