@@ -85,7 +85,7 @@ __host__ __device__ inline FastLayout fast_layout(int nr, int S, int ne) {
     L.ldd = al4(nm);                         // distance-table row stride: rows start 16-byte aligned, so the row-sum loop reads four columns per LDS.128
     int q = 0;
     L.D = q; q += nm * L.ldd;
-    {   // the S - ne resampled rows (iteration 0 reads the constant theta0 table straight from global memory); the region is also borrowed by the
+    {   // the S - ne resampled rows (iteration 0: the first S - ne rows of the constant theta0 table; the rest sit in the elite buffer); the region is also borrowed by the
         // mother features while D is built and by the centered elites xc between the elite gather and the covariance (the rows are dead then)
         int n = (S - ne) * L.ldt;
         if (nm * 2 * NV > n) n = nm * 2 * NV;
@@ -560,7 +560,8 @@ template <int d> __device__ __forceinline__ void icl_chol_lookahead(float* __res
 // FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
 // SC / NEC = compile-time copies of the inner CEM's sample / elite counts (0 = read them from the configuration): with the reference's sizes (100 / 11) baked in, the
 // whole shared-memory layout folds into immediate offsets, which takes the address arithmetic the 56-register cap otherwise re-derives in every phase out of the kernel
-template <int NR, bool LAT, bool FM = false, int SC = 0, int NEC = 0>
+// LA = two-warp look-ahead Cholesky (icl_chol_lookahead) instead of the one-warp panel factorisation (MPCMMD_CHOL=la, measured variant)
+template <int NR, bool LAT, bool FM = false, int SC = 0, int NEC = 0, bool LA = false>
 __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -595,7 +596,9 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         }
         __syncthreads();
     }
-    // ---- iteration 0 evaluates the S rows of theta0 (a constant table, read in place from global memory); later iterations the S - ne resampled rows
+    // ---- iteration 0 evaluates the S rows of theta0, later iterations the S - ne resampled rows.  theta0 (a constant table) is staged in shared memory once: its first
+    //      S - ne rows into the row region, the last ne into the elite buffer (no elites exist before the first selection), so every iteration reads its rows with
+    //      shared-memory loads at a compile-time stride -- new row s lives at th[s] for s < S - ne, else at eth[s - (S - ne)] (only iteration 0 has such rows)
     // covariance task of this thread: row cr, columns 4*cg .. 4*cg+3 (lower triangle in groups of four; tasks beyond nt wrap)
     int cr = -1, cg = 0, cr2 = -1, cg2 = 0;
     {
@@ -606,15 +609,23 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
             for (int q4 = 0; q4 <= r / 4; q4++) { if (t == tid) { cr = r; cg = q4; } if (t == tid + nt) { cr2 = r; cg2 = q4; } t++; }
         }
     }
+    {
+        const int nrow0 = S - ne;
+#pragma unroll 1
+        for (int i = tid; i < S * d; i += nt) {
+            const int s0 = i / d, q = i - s0 * d;
+            (s0 < nrow0 ? th + s0 * ldt : eth + (s0 - nrow0) * ldt)[q] = c.theta0[i];
+        }
+    }
     __syncthreads();
     float* resb = a.res_beta + (size_t)g * c.iters_in;
 #pragma unroll 1
     for (int it = 0; it < c.iters_in; it++) {
         const int n_old = it == 0 ? 0 : ne, n_new = S - n_old;
-        const float* rows = it == 0 ? c.theta0 : th; const int rstride = it == 0 ? d : ldt;      // where this iteration's new rows live
+        const int nrow = S - ne;
         // -- evaluate the new rows (the elites keep last iteration's cost: same row => same arithmetic => same bits)
 #pragma unroll 1
-        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR, FM, LDD>(c, rows + s * rstride, D, betas + s * NR, idxs + s);
+        for (int s = tid; s < n_new; s += nt) cost[s] = beta_sample_fast<NR, FM, LDD>(c, s < nrow ? th + s * ldt : eth + (s - nrow) * ldt, D, betas + s * NR, idxs + s);
         __syncthreads();
         // -- stable argsort, first ne entries: candidate j < n_old is elite j, else new row j - n_old  [compute_beta.py:56]
         if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);
@@ -629,7 +640,8 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
             for (int el = 0; el < ICF_MAX_NE; el++) {
                 if (el < ne) {
                     const int p = perm[el];
-                    v[el] = p < n_old ? eth[p * ldt + tid] : rows[(p - n_old) * rstride + tid];
+                    const int pn = p - n_old;          // new row index; rows beyond the row region exist in iteration 0 only (staged in the elite buffer)
+                    v[el] = (p < n_old ? eth + p * ldt : pn < nrow ? th + pn * ldt : eth + (pn - nrow) * ldt)[tid];
                     s = s + v[el];
                 }
             }
@@ -666,18 +678,14 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel).  The two-warp look-ahead variant of the
         //    latency kernel (icl_chol_lookahead, partial sums in the dead row region) was measured here too (-DICF_CHOL_LOOKAHEAD): 155.7 vs 153.6 ms per 200-episode
         //    solve -- under the 56-register cap it spills, and with 12 chains per SM the phase is bound by issued instructions, not by warp 0's critical path.
-#ifdef ICF_CHOL_LOOKAHEAD
-        if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane);
-#else
-        if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
-#endif
+        if constexpr (LA) { if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane); }
+        else if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].
         //    LT[k][q] = 0 for q < k, so a term with k > q adds an exact zero and whole float4 groups can be used; the k loop is rolled in
         //    two ranges whose (static) column-group sets skip most of the zero triangle.
         {
             constexpr int NG = (d + 3) / 4;
-            const int nrow = S - ne;
             const float* zT = c.zb_iterT + (size_t)it * d * nrow;
 #pragma unroll 1
             for (int r = tid; r < nrow; r += nt) {
@@ -721,6 +729,7 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
 // sample's noisy controls (same arithmetic as the mother rollout => same bits) with the obstacle / lane maxima folded in, then one thread per
 // sample evaluates the three MMD values.  The mother rollouts themselves are never stored.
 #define OPT_RISK_THREADS 128
+template <bool SORTED = false>
 __global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs ra) {
     __shared__ float vals[3 * OPT_RISK_THREADS];
     const RiskArgs& a = ra.r;
@@ -733,7 +742,7 @@ __global__ void __launch_bounds__(OPT_RISK_THREADS) k_opt_risk(DCfg c, RollArgs 
         const float* ct = ra.ctrl + (size_t)g * 2 * n;
         float m, l, u;
         if (ra.fold_risk) { const float* mr = ra.mrisk + ((size_t)g * nr * nr + mi) * 3; m = mr[0]; l = mr[1]; u = mr[2]; }     // folded by the mother rollout itself
-        else rollout_risk<false>(c, a, g, e, 0, ct + (mi / nr) * np, ct + n + (mi % nr) * np, a.state0 + e * 5,
+        else rollout_risk<false, SORTED>(c, a, g, e, 0, ct + (mi / nr) * np, ct + n + (mi % nr) * np, a.state0 + e * 5,
                                  a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
         vals[tid] = m; vals[OPT_RISK_THREADS + tid] = l; vals[2 * OPT_RISK_THREADS + tid] = u;
     }
@@ -1000,7 +1009,7 @@ __device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float*
     }
 }
 
-template <int NR>
+template <int NR, int SC = 0, int NEC = 0>          // SC / NEC: compile-time sample / elite counts, see k_inner_cem_fast
 __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -1008,7 +1017,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
     if (g >= a.n_samples) return;
     constexpr int nm = NR * NR, d = nm + 1, NG = (d + 3) / 4, LDD = (nm + 3) & ~3;       // = FastLayout::ldd
     const int tid = threadIdx.x, nt = ICL_THREADS, warp = tid >> 5, lane = tid & 31;
-    const int S = c.S_in, ne = c.n_el_in;
+    const int S = SC ? SC : c.S_in, ne = NEC ? NEC : c.n_el_in;
     const FastLayout L = fast_layout(NR, S, ne);
     const int ldt = L.ldt, ldc = L.ldc;
     float* D = sm + L.D; float* th = sm + L.th; float* cost = sm + L.cost; float* betas = ra.bscratch + (size_t)g * S * (NR + 1); int* idxs = (int*)(betas + S * NR);

@@ -183,20 +183,24 @@ __host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R, 
 }
 
 // noisy control pair of element el = row * np + t of sample g  [cem_helper.py:405-443 / 470-508]
+// NZ = the noise path the launch needs, fixed at compile time so that a kernel carries only that path's code and registers: 0 Gaussian, 1 Beta draws replayed from the
+// per-episode candidate table (every beta-noise solve), 2 decided at run time (injected draws / direct sampler of the stage entry points)
+enum { NZ_GAUSS = 0, NZ_BETA_TABLE = 1, NZ_ANY = 2 };
+template <int NZ = NZ_ANY>
 __device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, int g, int e, int el, int t, int n, float& an, float& sn) {
     const float av = a.acc[(size_t)g * T_ + t], sv = a.steer[(size_t)g * T_ + t];
     const float* z3 = a.z3 + e * a.z_stride;
     float pa, ps;
-    if (c.noise_kind == 0) {
+    if (NZ == NZ_GAUSS || (NZ == NZ_ANY && c.noise_kind == 0)) {
         pa = (c.sigma_acc * fabsf(av)) * (a.z1 + e * a.z_stride)[el];
         ps = (c.sigma_steer * fabsf(sv)) * (a.z2 + e * a.z_stride)[el];
     } else {
         const uint32_t* keys = a.keys + e * a.key_stride;
         dr::Key k1, k2; k1.k0 = keys[0]; k1.k1 = keys[1]; k2.k0 = keys[2]; k2.k1 = keys[3];
         float b1, b2;
-        if (a.binj1) {
+        if (NZ == NZ_ANY && a.binj1) {
             b1 = a.binj1[(size_t)g * n + el]; b2 = a.binj2[(size_t)g * n + el];
-        } else if (a.btab) {
+        } else if (NZ == NZ_BETA_TABLE || a.btab) {
             const float* bt = a.btab + e * a.btab_stride;
             b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
             b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
@@ -239,7 +243,9 @@ __global__ void k_obs_sort(const float* __restrict__ x_obs, const float* __restr
 // each evaluated on the state BEFORE step t (the recorded point).  The maxima are order independent (NaN propagates either way), so this equals
 // the reference's "roll out, then reduce" [costs.py:50-71].  FLY: the controls of row `row` are drawn inside the loop (costs with one control row
 // per rollout); otherwise they are read from a / s.
-template <bool FLY>
+// SORTED = the launch has sorted obstacle windows (num_obs > OBS_SORT_MIN); a separate instantiation, so that the few-obstacle kernels do not carry the
+// window search's code and registers (the combined kernel took k_rollouts<ROLL_FLY> from 341 to 549 us per 20 000-sample launch of configs[1])
+template <bool FLY, bool SORTED = false, int NZ = NZ_ANY>
 __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, int g, int e, int row, const float* a, const float* s,
                                              const float* st0, const float* __restrict__ xo, const float* __restrict__ yo, float& m, float& l, float& u) {
     float x = st0[0], y = st0[1], vx = st0[2], vy = st0[3], psi = st0[4];
@@ -248,8 +254,8 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
 #pragma unroll 1
     for (int t = 0; t < np; t++) {
         float at, st;
-        if (FLY) { noisy_control(c, A, g, e, row * np + t, t, n, at, st); st = dm::tan_(st); } else { at = a[t]; st = s[t]; }      // s = tan(steer) when staged
-        if (A.sx_obs && x == x && y == y && fabsf(x) < 1.0e4f && !A.obs_nan[e * T_ + t]) {
+        if (FLY) { noisy_control<NZ>(c, A, g, e, row * np + t, t, n, at, st); st = dm::tan_(st); } else { at = a[t]; st = s[t]; }      // s = tan(steer) when staged
+        if (SORTED && A.sx_obs && x == x && y == y && fabsf(x) < 1.0e4f && !A.obs_nan[e * T_ + t]) {
             const float* xs = A.sx_obs + ((size_t)e * T_ + t) * c.O; const float* ys = A.sy_obs + ((size_t)e * T_ + t) * c.O;
             const float xl = x - c.obs_win, xh = x + c.obs_win;
             int lo = 0, n_ = c.O;
@@ -272,7 +278,7 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
 
 // MODE 0: mmd_opt; 1: num_reduced-rollout costs, throughput regime; 2: the same, latency regime.  Three instantiations keep each launch's code small.
 enum { ROLL_OPT = 0, ROLL_FLY = 1, ROLL_STAGED = 2 };
-template <int MODE>
+template <int MODE, bool SORTED = false, int NZ = NZ_ANY>
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
-            float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
+            float an, sn; noisy_control<NZ>(c, a, g, g / a.B, el, el % np, n, an, sn);
             const float tn = dm::tan_(sn);                     // the rollouts (and k_opt_risk's re-rolls) only ever need tan(steer)
             sm[ls * 2 * n + el] = an; sm[ls * 2 * n + n + el] = tn;
             ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = tn;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
-            float an, sn; noisy_control(c, a, g, g / a.B, el, el % np, n, an, sn);
+            float an, sn; noisy_control<NZ>(c, a, g, g / a.B, el, el % np, n, an, sn);
             sm[ls * per + 4 * tail + el] = an; sm[ls * per + 4 * tail + n + el] = dm::tan_(sn);
         }
         __syncthreads();
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
         for (int i = tid; i < ns * R; i += nt) {
             const int ls = i / R, r = i % R, g = g0 + ls, e = g / a.B;
             float m, l, u;
-            rollout_risk<true>(c, a, g, e, r, nullptr, nullptr, a.state0 + e * 5, a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
+            rollout_risk<true, SORTED, NZ>(c, a, g, e, r, nullptr, nullptr, a.state0 + e * 5, a.x_obs + (size_t)e * c.O * T_, a.y_obs + (size_t)e * c.O * T_, m, l, u);
             float* cst = sm + ls * per;
             cst[r] = m; cst[tail + r] = l; cst[2 * tail + r] = u;
         }

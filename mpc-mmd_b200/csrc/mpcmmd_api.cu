@@ -44,7 +44,7 @@ static int raise_smem(int device, const void* fn, size_t bytes, bool carveout_ma
 }
 extern "C" int mpcmmd_version(void) { return 100; }
 
-#define MAX_GROUPS 4
+#define MAX_GROUPS 8
 struct mpcmmd_handle_s {
     int device = 0;
     mpcmmd_config cfg;         // host copy (matrix pointers are NOT valid after create)
@@ -77,7 +77,7 @@ struct mpcmmd_handle_s {
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream[MAX_GROUPS - 1] = {};   // further branches of a solve graph whose episodes are split into groups (see solve_groups)
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS - 1] = {};
-    int groups_override = 0;                 // MPCMMD_GROUPS=1..4: force the number of episode groups of a solve graph (0 = automatic)
+    int groups_override = 0;                 // MPCMMD_GROUPS=1..8: force the number of episode groups of a solve graph (0 = automatic)
     int prio_mode = 0;                       // MPCMMD_PRIO=0|1|2 (experiment, default off): highest stream priority on the kernel nodes of mmd_opt graphs (1) / of the other cost functions' graphs (2)
 };
 
@@ -176,6 +176,13 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     if (kind == MPCMMD_COST_MMD_OPT && inner_cem_is_fast(d)) { const size_t v = roll_smem_for(d, kind, 1, 0, 1); if (v > c) c = v; }      // latency regime (num_reduced <= 5 only): positions of one sample's mother rollouts
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
+// k_rollouts instantiation of a launch: mode (ROLL_*), noise path (NZ_*), sorted obstacle windows (ROLL_FLY only; Gaussian or the run-time noise path)
+static const void* rollouts_kernel(int mode, int nz, int sorted) {
+    if (mode == ROLL_OPT) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_OPT, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_OPT, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_OPT, false, NZ_ANY>;
+    if (mode == ROLL_STAGED) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_STAGED, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_STAGED, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_STAGED, false, NZ_ANY>;
+    if (sorted) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_FLY, true, NZ_GAUSS> : (const void*)k_rollouts<ROLL_FLY, true, NZ_ANY>;
+    return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_FLY, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_FLY, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_FLY, false, NZ_ANY>;
+}
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
 enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7, INNER_BIG = 8, INNER_LAT512 = 9 };
 #define MPCMMD_BIG_SCRATCH_BYTES ((size_t)8 << 30)      // global chain state of k_inner_cem_big held at a time (num_reduced 40: 23 MB per chain)
@@ -202,11 +209,18 @@ static SplitKernels split_kernels(int nr) {
 }
 static size_t split_eval_smem(const DCfg& d) { const int dd = d.nm + 1; return (size_t)(al4(d.nm * d.nm) + (dd + 1) * al4(dd)) * sizeof(float); }
 static size_t split_update_smem(const DCfg& d) { return (size_t)ICU_WARPS * upd_layout(d.nr).total * sizeof(float); }
+static bool g_chol_la = false;       // MPCMMD_CHOL=la (read at create): look-ahead Cholesky build of the specialised throughput kernel
 static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_WARP) switch (d.nr) {
         case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
     }
-    if (kind == INNER_CTA && d.nr == 5 && d.S_in == 100 && d.n_el_in == 11) return k_inner_cem_fast<5, false, false, 100, 11>;      // the reference's sizes as compile-time constants
+    if (d.nr == 5 && d.S_in == 100 && d.n_el_in == 11) {          // the reference's sizes as compile-time constants
+        if (kind == INNER_CTA && g_chol_la) return k_inner_cem_fast<5, false, false, 100, 11, true>;
+        if (kind == INNER_CTA) return k_inner_cem_fast<5, false, false, 100, 11>;
+        if (kind == INNER_CTA_LAT) return k_inner_cem_fast<5, true, false, 100, 11>;
+        if (kind == INNER_CTA_FASTMATH) return k_inner_cem_fast<5, false, true, 100, 11>;
+        if (kind == INNER_LAT512) return k_inner_cem_lat<5, 100, 11>;
+    }
     if (kind == INNER_CTA) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, false>; case 3: return k_inner_cem_fast<3, false>; case 4: return k_inner_cem_fast<4, false>; case 5: return k_inner_cem_fast<5, false>;
     }
@@ -386,8 +400,10 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
     {
         size_t rs = nr <= MPCMMD_MAX_NR_OPT ? roll_smem(h, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(h, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory");
-        if (raise_smem(device, (const void*)k_rollouts<ROLL_OPT>, rs) || raise_smem(device, (const void*)k_rollouts<ROLL_FLY>, rs) ||
-            raise_smem(device, (const void*)k_rollouts<ROLL_STAGED>, rs)) return fail("k_rollouts smem opt-in failed");
+        for (int mode = 0; mode < 3; mode++) for (int nz = 0; nz < 3; nz++) for (int so = 0; so < 2; so++) {
+            const void* f = rollouts_kernel(mode, nz, so);
+            if (f && raise_smem(device, f, rs)) return fail("k_rollouts smem opt-in failed");
+        }
     }
     {
         const char* mode = getenv("MPCMMD_INNER_CEM");       // test / profiling override of the kernel choice
@@ -404,6 +420,7 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
             if (raise_smem(device, (const void*)pipe_kernel(d.nr, h->pipe_minb), pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), true)) return fail("k_inner_cem_pipe smem opt-in failed");
         }
         { const char* mm = getenv("MPCMMD_MATH"); h->fast_math = mm && !strcmp(mm, "fast"); }
+        { const char* cl = getenv("MPCMMD_CHOL"); g_chol_la = cl && !strcmp(cl, "la"); }
         for (int kind = INNER_WARP; kind <= INNER_LAT512; kind++) {
             if (kind == INNER_SPLIT || kind == INNER_PIPE || kind == INNER_BIG) continue;
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
@@ -431,8 +448,8 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
         // never wait for an SM to drain before its L1 / shared split can change
         const char* cv = getenv("MPCMMD_CARVE");
         if (cv) {
-            const void* fns[] = {(const void*)k_project, (const void*)k_rollouts<ROLL_OPT>, (const void*)k_rollouts<ROLL_FLY>, (const void*)k_rollouts<ROLL_STAGED>,
-                                 (const void*)k_opt_risk, (const void*)k_select, (const void*)k_noise, (const void*)k_init, (const void*)k_boundary};
+            const void* fns[] = {(const void*)k_project, rollouts_kernel(ROLL_OPT, NZ_BETA_TABLE, 0), rollouts_kernel(ROLL_FLY, NZ_BETA_TABLE, 0), rollouts_kernel(ROLL_STAGED, NZ_BETA_TABLE, 0),
+                                 (const void*)k_opt_risk<false>, (const void*)k_select, (const void*)k_noise, (const void*)k_init, (const void*)k_boundary};
             for (const void* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv) == 1 ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault);
         }
     }
@@ -540,9 +557,11 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
     {
         if (ra.fold_risk) ra.spb = 1;
         const int grid = (r.n_samples + ra.spb - 1) / ra.spb; const size_t rsm = roll_smem_for(d, r.cost_kind, ra.spb, ra.stage_ctrl, ra.fold_risk);
-        if (opt) k_rollouts<ROLL_OPT><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
-        else if (ra.stage_ctrl) k_rollouts<ROLL_STAGED><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
-        else k_rollouts<ROLL_FLY><<<grid, ROLL_THREADS, rsm, s>>>(d, ra);
+        const int nz = d.noise_kind == 0 ? NZ_GAUSS : (r.btab && !r.binj1) ? NZ_BETA_TABLE : NZ_ANY;
+        const int mode = opt ? ROLL_OPT : ra.stage_ctrl ? ROLL_STAGED : ROLL_FLY;
+        const void* fk = rollouts_kernel(mode, nz, mode == ROLL_FLY && r.sx_obs);
+        void* kargs[] = {(void*)&d, (void*)&ra};
+        CK(cudaLaunchKernel(fk, dim3(grid), dim3(ROLL_THREADS), kargs, rsm, s));
     }
     if (n_launch) *n_launch = 1;
     if (opt && kind == INNER_BIG) {
@@ -557,7 +576,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         if (n_launch) *n_launch = nl;
     } else if (opt && kind == INNER_PIPE) {
         pipe_kernel(d.nr, h->pipe_minb)<<<(r.n_samples + 1) / 2, ICP_THREADS, pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), s>>>(d, ra, h->throws);
-        { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
+        { const int ospb = OPT_RISK_THREADS / d.nr; if (r.sx_obs) k_opt_risk<true><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); else k_opt_risk<false><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
         if (n_launch) *n_launch = 3;
     } else if (opt && kind == INNER_SPLIT) {
         const SplitKernels sk = split_kernels(d.nr);
@@ -571,7 +590,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
             sk.eval<<<r.n_samples, (it == 0 && d.S_in > ICE_THREADS) ? 128 : ICE_THREADS, se, s>>>(d, sa, it);
             sk.update<<<(r.n_samples + ICU_WARPS - 1) / ICU_WARPS, ICU_WARPS * 32, su, s>>>(d, sa, it);
         }
-        { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
+        { const int ospb = OPT_RISK_THREADS / d.nr; if (r.sx_obs) k_opt_risk<true><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); else k_opt_risk<false><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
         if (n_launch) *n_launch = 3 + 2 * d.iters_in;
     } else if (opt) {
         const size_t sm = inner_cem_smem_kind(d, kind);
@@ -579,7 +598,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         else f<<<r.n_samples, kind == INNER_LAT512 ? ICL_THREADS : (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH) ? ICF_THREADS : risko_threads(d.nr), sm, s>>>(d, ra);
         if (n_launch) *n_launch = 2;
         if (kind == INNER_CTA || kind == INNER_CTA_LAT || kind == INNER_CTA_FASTMATH || kind == INNER_LAT512) {
-            { const int ospb = OPT_RISK_THREADS / d.nr; k_opt_risk<<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
+            { const int ospb = OPT_RISK_THREADS / d.nr; if (r.sx_obs) k_opt_risk<true><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); else k_opt_risk<false><<<(r.n_samples + ospb - 1) / ospb, OPT_RISK_THREADS, 0, s>>>(d, ra); }
             if (n_launch) *n_launch = 3;
         }
     }
@@ -631,7 +650,8 @@ static int solve_groups(const mpcmmd_handle_s* h, int kind, int n_ep) {
     if (h->groups_override >= 1 && h->groups_override <= MAX_GROUPS) return h->groups_override < n_ep ? h->groups_override : n_ep;
     const long long chains = (long long)n_ep * h->d.B;
     if (kind != MPCMMD_COST_MMD_OPT || !inner_cem_is_fast(h->d) || chains <= 6LL * h->sm_count || chains > 36LL * h->sm_count) return 1;
-    return chains > 12LL * h->sm_count ? 3 : 2;
+    const int G = chains > 12LL * h->sm_count ? 3 : 2;
+    return G < n_ep ? G : n_ep;              // never an empty group (large num_batch: few episodes, many chains)
 }
 static int get_graph(mpcmmd_handle_s* h, int kind, int n_ep, cudaGraphExec_t* out) {
     auto key = std::make_pair(kind, n_ep);

@@ -3,7 +3,7 @@
 (one handle + stream per cost function, concurrent) under the graph-level switches of mpcmmd_create:
   MPCMMD_GROUPS = episode groups (branches) of a solve graph, MPCMMD_PRIO = highest stream priority on the kernel nodes of mmd_opt graphs,
   MPCMMD_CARVE  = maximum shared-memory carve-out preference on every kernel of a solve.
-usage: overlap_probe.py [E ...]      (writes gpurun_out/overlap_probe.json)"""
+usage: [PROBE_GROUPS=1,2,3,4] [PROBE_PRIOS=0,1,2] [PROBE_CARVES=0,1] overlap_probe.py [E ...]      (writes gpurun_out/overlap_probe.json)"""
 import itertools
 import json
 import os
@@ -41,7 +41,10 @@ def timed(fn, n=9):
 
 out = {}
 Es = [int(a) for a in sys.argv[1:]] or [25, 50, 100]
-combos = [dict(MPCMMD_GROUPS=g, MPCMMD_PRIO=p, MPCMMD_CARVE=c) for c, p, g in itertools.product("0", "012", ("2", "3"))]
+GROUPS = os.environ.get("PROBE_GROUPS", "1,2,3,4").split(",")
+PRIOS = os.environ.get("PROBE_PRIOS", "0").split(",")
+CARVES = os.environ.get("PROBE_CARVES", "0").split(",")
+combos = [dict(MPCMMD_GROUPS=g, MPCMMD_PRIO=p, MPCMMD_CARVE=c) for c, p, g in itertools.product(CARVES, PRIOS, GROUPS)]
 for E in Es:
     host = None
     for env in combos:
