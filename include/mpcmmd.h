@@ -131,6 +131,10 @@ int mpcmmd_fp32_peak(int device, float *tflops, int *sm_count);
 /* Measured special-function-unit peaks (thread-level operations per second / 1e9): gops[0] = ex2.approx (MUFU.EX2), gops[1] = IEEE
  * div.rn.f32, gops[2] = IEEE sqrt.rn.f32 -- the denominators for the XU-bound kernels. */
 int mpcmmd_xu_peaks(int device, float *gops);
+/* Exhaustive device self-check of the two IEEE shortcuts the inner-CEM kernels use (csrc/dmath.cuh): over ALL 2^32 float bit patterns,
+ * mismatches[0] = dm::sqrt_rcp's root vs sqrtf, [1] = its reciprocal vs 1.0f / sqrtf, [2] = dm::div10 vs x / 10.0f (NaN == NaN).
+ * All three must be 0: the shortcuts are then the IEEE operations of the arithmetic contract (S/compute_beta.py:61-63: jnp.cov, cholesky). */
+int mpcmmd_selfcheck_ieee(int device, unsigned long long *mismatches /* [3], host */);
 
 /* ---- stage entry points (teacher-forced parity tests; all DEVICE pointers, synchronous) ---- */
 

@@ -228,8 +228,8 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
         float acc = K[j][j] + 0.05f;
 #pragma unroll
         for (int k = 0; k < j; k++) acc = fmaf(-Lm[j][k], Lm[j][k], acc);
-        const float dd = sqrtf(acc);
-        Lm[j][j] = dd; rd[j] = 1.0f / dd;
+        float dd; dm::sqrt_rcp(acc, dd, rd[j]);
+        Lm[j][j] = dd;
 #pragma unroll
         for (int i = j + 1; i < NR; i++) {
             float aa = K[i][j];
@@ -428,13 +428,14 @@ __device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc_, 
         const float b10 = __shfl_sync(FULL, a0, j0 + 1), b11 = __shfl_sync(FULL, a1, j0 + 1);
         const float b20 = __shfl_sync(FULL, a0, j0 + 2), b21 = __shfl_sync(FULL, a1, j0 + 2), b22 = __shfl_sync(FULL, a2, j0 + 2);
         const float b30 = __shfl_sync(FULL, a0, j0 + 3), b31 = __shfl_sync(FULL, a1, j0 + 3), b32 = __shfl_sync(FULL, a2, j0 + 3), b33 = __shfl_sync(FULL, a3, j0 + 3);
-        const float d0 = sqrtf(b00), r0 = 1.0f / d0;
+        float d0, r0, d1, r1, d2, r2, d3, r3;
+        dm::sqrt_rcp(b00, d0, r0);
         const float l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
-        const float d1 = sqrtf(fmaf(-l10, l10, b11)), r1 = 1.0f / d1;
+        dm::sqrt_rcp(fmaf(-l10, l10, b11), d1, r1);
         const float l21 = fmaf(-l20, l10, b21) * r1, l31 = fmaf(-l30, l10, b31) * r1;
-        const float d2 = sqrtf(fmaf(-l21, l21, fmaf(-l20, l20, b22))), r2 = 1.0f / d2;
+        dm::sqrt_rcp(fmaf(-l21, l21, fmaf(-l20, l20, b22)), d2, r2);
         const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b32)) * r2;
-        const float d3 = sqrtf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33)))), r3 = 1.0f / d3;
+        dm::sqrt_rcp(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33))), d3, r3);
         // own row: L[r][j0 + u]; on the diagonal the pivot itself, above it nothing
         float e0 = a0 * r0;
         a1 = fmaf(-e0, l10, a1); float e1 = a1 * r1;
@@ -479,7 +480,7 @@ __device__ __forceinline__ void icf_cov_task(const float* __restrict__ xc, float
     }
     float o[4]; pk::unpack(a01, o[0], o[1]); pk::unpack(a23, o[2], o[3]);
 #pragma unroll
-    for (int u = 0; u < 4; u++) { o[u] = o[u] / nm1; if (4 * q4 + u == r) o[u] = o[u] + 0.05f; }
+    for (int u = 0; u < 4; u++) { o[u] = (ne == 11) ? dm::div10(o[u]) : o[u] / nm1; if (4 * q4 + u == r) o[u] = o[u] + 0.05f; }
     *reinterpret_cast<float4*>(C + r * ldc + 4 * q4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
@@ -862,8 +863,8 @@ __device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sig
         float acc = K[j][j] + 0.05f;
 #pragma unroll
         for (int k = 0; k < j; k++) acc = fmaf(-Lm[j][k], Lm[j][k], acc);
-        const float dd = sqrtf(acc);
-        Lm[j][j] = dd; rd[j] = 1.0f / dd;
+        float dd; dm::sqrt_rcp(acc, dd, rd[j]);
+        Lm[j][j] = dd;
 #pragma unroll
         for (int i = j + 1; i < NR; i++) {
             float aa = K[i][j];
@@ -973,13 +974,14 @@ __device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float*
         const float b10 = __shfl_sync(FULL, a0, j0 + 1), b11 = __shfl_sync(FULL, a1, j0 + 1);
         const float b20 = __shfl_sync(FULL, a0, j0 + 2), b21 = __shfl_sync(FULL, a1, j0 + 2), b22 = __shfl_sync(FULL, a2, j0 + 2);
         const float b30 = __shfl_sync(FULL, a0, j0 + 3), b31 = __shfl_sync(FULL, a1, j0 + 3), b32 = __shfl_sync(FULL, a2, j0 + 3), b33 = __shfl_sync(FULL, a3, j0 + 3);
-        const float d0 = sqrtf(b00), r0 = 1.0f / d0;
+        float d0, r0, d1, r1, d2, r2, d3, r3;
+        dm::sqrt_rcp(b00, d0, r0);
         const float l10 = b10 * r0, l20 = b20 * r0, l30 = b30 * r0;
-        const float d1 = sqrtf(fmaf(-l10, l10, b11)), r1 = 1.0f / d1;
+        dm::sqrt_rcp(fmaf(-l10, l10, b11), d1, r1);
         const float l21 = fmaf(-l20, l10, b21) * r1, l31 = fmaf(-l30, l10, b31) * r1;
-        const float d2 = sqrtf(fmaf(-l21, l21, fmaf(-l20, l20, b22))), r2 = 1.0f / d2;
+        dm::sqrt_rcp(fmaf(-l21, l21, fmaf(-l20, l20, b22)), d2, r2);
         const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b32)) * r2;
-        const float d3 = sqrtf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33)))), r3 = 1.0f / d3;
+        dm::sqrt_rcp(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b33))), d3, r3);
         float e0 = a0 * r0;
         a1 = fmaf(-e0, l10, a1); float e1 = a1 * r1;
         a2 = fmaf(-e1, l21, fmaf(-e0, l20, a2)); float e2 = a2 * r2;

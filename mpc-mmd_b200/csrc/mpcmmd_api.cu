@@ -1041,6 +1041,37 @@ __global__ void __launch_bounds__(256) k_xu_peak(float* out, int iters, float a)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
+// ---- exhaustive check of the IEEE shortcuts of dmath.cuh (dm::sqrt_rcp, dm::div10) against sqrtf / the IEEE division on every float bit pattern
+__global__ void k_selfcheck_ieee(unsigned long long* bad /* [3] */) {
+    unsigned long long b0 = 0, b1 = 0, b2 = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ULL << 32); i += stride) {
+        const float a = dm::u2f((uint32_t)i);
+        float dd, rd; dm::sqrt_rcp(a, dd, rd);
+        const float ds = sqrtf(a), rs = 1.0f / ds;
+        b0 += !(dm::f2u(dd) == dm::f2u(ds) || (dd != dd && ds != ds));
+        b1 += !(dm::f2u(rd) == dm::f2u(rs) || (rd != rd && rs != rs));
+        const float q = dm::div10(a), qs = a / 10.0f;
+        b2 += !(dm::f2u(q) == dm::f2u(qs) || (q != q && qs != qs));
+    }
+    if (b0) atomicAdd(bad, b0);
+    if (b1) atomicAdd(bad + 1, b1);
+    if (b2) atomicAdd(bad + 2, b2);
+}
+extern "C" int mpcmmd_selfcheck_ieee(int device, unsigned long long* mismatches /* [3], host */) {
+    if (!mismatches) return fail("mpcmmd_selfcheck_ieee: null pointer");
+    CK(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+    k_selfcheck_ieee<<<148 * 8, 256>>>(d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    return 0;
+}
+
 extern "C" int mpcmmd_xu_peaks(int device, float* gops /* [3] */) {
     if (!gops) return fail("mpcmmd_xu_peaks: null pointer");
     CK(cudaSetDevice(device));

@@ -33,7 +33,7 @@ class MpcmmdOut(C.Structure):
 
 
 EXPORTS = ("mpcmmd_last_error", "mpcmmd_version", "mpcmmd_create", "mpcmmd_destroy", "mpcmmd_solve", "mpcmmd_solve_host",
-           "mpcmmd_last_launch_count", "mpcmmd_inner_cem_path", "mpcmmd_profile_solve", "mpcmmd_fp32_peak", "mpcmmd_xu_peaks", "mpcmmd_math_vec", "mpcmmd_rng_normal", "mpcmmd_rng_beta", "mpcmmd_get_tables",
+           "mpcmmd_last_launch_count", "mpcmmd_inner_cem_path", "mpcmmd_profile_solve", "mpcmmd_fp32_peak", "mpcmmd_xu_peaks", "mpcmmd_selfcheck_ieee", "mpcmmd_math_vec", "mpcmmd_rng_normal", "mpcmmd_rng_beta", "mpcmmd_get_tables",
            "mpcmmd_stage_project", "mpcmmd_stage_risk", "mpcmmd_stage_risk_injected", "mpcmmd_stage_init", "mpcmmd_stage_select", "mpcmmd_stage_noise", "mpcmmd_validate_host")
 
 _lib = None
@@ -64,6 +64,7 @@ def load():
     lib.mpcmmd_profile_solve.argtypes = [V, C.c_int, C.c_int, V, V]
     lib.mpcmmd_fp32_peak.argtypes = [C.c_int, V, V]
     lib.mpcmmd_xu_peaks.argtypes = [C.c_int, V]
+    lib.mpcmmd_selfcheck_ieee.argtypes = [C.c_int, V]
     lib.mpcmmd_math_vec.argtypes = [C.c_int, V, V, V, C.c_int, C.c_int]
     lib.mpcmmd_rng_normal.argtypes = [C.c_uint32, C.c_uint32, C.c_int, V, C.c_int]
     lib.mpcmmd_rng_beta.argtypes = [C.c_uint32, C.c_uint32, V, V, C.c_int, V, C.c_int]

@@ -339,6 +339,14 @@ def fp32_peak(device=0):
     return float(tf.value), int(sm.value)
 
 
+def selfcheck_ieee(device=0):
+    """(sqrt, reciprocal-of-sqrt, divide-by-10) mismatch counts of the device's IEEE shortcuts against sqrtf / division over all 2^32 float bit patterns."""
+    lib = B.load()
+    m = (C.c_ulonglong * 3)()
+    B.check(lib.mpcmmd_selfcheck_ieee(int(device), m))
+    return int(m[0]), int(m[1]), int(m[2])
+
+
 def xu_peaks(device=0):
     """dict(ex2_gops, div_gops, sqrt_gops): measured MUFU.EX2 / IEEE division / IEEE square-root throughput (thread-level Gop/s)."""
     lib = B.load()

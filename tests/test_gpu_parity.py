@@ -32,6 +32,13 @@ MATH_RANGES = {"exp": (-100.0, 90.0), "log": (1e-42, 1e6), "log1p": (-0.9999999,
                "tan": (-1.6, 1.6), "atan": (-1e4, 1e4), "erfinv": (-0.99999994, 0.99999994)}
 
 
+def test_ieee_shortcuts_exhaustive(mods):
+    """dm::sqrt_rcp (one range check for the pivot's square root and its reciprocal) and dm::div10 (covariance / (num_elite - 1)) are the IEEE operations of
+    the contract: compared on the device with sqrtf, 1.0f / sqrtf and x / 10.0f over ALL 2^32 float bit patterns (NaN == NaN), zero mismatches."""
+    cem_impl, _ = mods
+    assert cem_impl.selfcheck_ieee(0) == (0, 0, 0)
+
+
 @pytest.mark.parametrize("fn", list(MATH_RANGES))
 def test_device_math_bit_exact(mods, fn):
     cem_impl, O = mods
