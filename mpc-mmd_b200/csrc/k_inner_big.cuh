@@ -51,10 +51,10 @@ __device__ __forceinline__ void big_topk(const float* __restrict__ row, int nm, 
 __device__ __forceinline__ float big_finish(const DCfg& c, int nr, int nm, const int* __restrict__ ti, float sigma, const float* __restrict__ rowsum,
                                             const float* __restrict__ D, float* __restrict__ beta, float* __restrict__ K, float* __restrict__ Lm,
                                             float* __restrict__ rd, float* __restrict__ u, float* __restrict__ w) {
-    const float rinv = 1.0f / sigma;
+    const dm::LapScale ls = dm::lap_scale(sigma);
     for (int i = 0; i < nr; i++) {
         K[i * nr + i] = 1.0f;
-        for (int j = 0; j < i; j++) { const float k = dm::exp_nonpos(-(D[(size_t)ti[i] * nm + ti[j]] * rinv)); K[i * nr + j] = k; K[j * nr + i] = k; }
+        for (int j = 0; j < i; j++) { const float k = dm::lap_(D[(size_t)ti[i] * nm + ti[j]], ls); K[i * nr + j] = k; K[j * nr + i] = k; }
     }
     for (int j = 0; j < nr; j++) {
         float acc = K[j * nr + j] + 0.05f;

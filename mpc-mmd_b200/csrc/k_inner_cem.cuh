@@ -21,30 +21,6 @@ __device__ __forceinline__ float hi(f2 v) { float a, b; unpack(v, a, b); return 
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// two dm::exp_nonpos at once (same operations in the same order per lane; the 2^n scaling is a float multiply so NaN survives)
-__device__ __forceinline__ f2 exp2_nonpos(float xa, float xb) {
-    const float MAGIC = 12582912.0f;
-    float sa, sb;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(sa) : "f"(xa), "f"(-87.0f));
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(sb) : "f"(xb), "f"(-87.0f));
-    const f2 xs = pack(sa, sb);
-    const f2 t = fma2(xs, dup(1.44269504088896341f), dup(MAGIC));
-    const f2 nf = add2(t, dup(-MAGIC));
-    f2 r = fma2(nf, dup(-0.693359375f), xs);
-    r = fma2(nf, dup(2.12194440e-4f), r);
-    f2 p = dup(1.9875691500e-4f);
-    p = fma2(p, r, dup(1.3981999507e-3f));
-    p = fma2(p, r, dup(8.3334519073e-3f));
-    p = fma2(p, r, dup(4.1665795894e-2f));
-    p = fma2(p, r, dup(1.6666665459e-1f));
-    p = fma2(p, r, dup(5.0000001201e-1f));
-    const f2 z = mul2(r, r);
-    const f2 y = add2(fma2(p, z, r), dup(1.0f));
-    float ta, tb; unpack(t, ta, tb);
-    // bits(t) = bits(MAGIC) + n and bits(MAGIC) << 23 == 0 (mod 2^32)  =>  (bits(t) << 23) + 0x3f800000 = bits(2^n)
-    const float sca = dm::u2f((dm::f2u(ta) << 23) + 0x3f800000u), scb = dm::u2f((dm::f2u(tb) << 23) + 0x3f800000u);
-    return mul2(y, pack(sca, scb));
-}
 // 16-byte shared-memory load from a 32-bit shared-window address (volatile: stays inside its loop trip, in program order with the barriers around the phase)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -54,20 +30,40 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 }  // namespace pk
 
-// Laplace kernel entries exp(-(d / sigma)) two at a time.  Exact contract (FM = false): sc2 = (1/sigma, 1/sigma), the product d * (1/sigma) is rounded, then the
-// contract's polynomial exp.  Fast-math (FM = true): sc2 = -(1/sigma) * log2(e) in both lanes and the exponentials run on the XU pipe (MUFU.EX2).
+// Laplace kernel entries k(d; sigma) two at a time (dm::lap_ per lane, operation for operation).  LapK carries the per-bandwidth constants: exact contract
+// (FM = false): sc2 = (-s2, -s2) and the distance cap; fast math (FM = true): sc2 = -(1/sigma) * log2(e) in both lanes, the exponentials run on the XU pipe (MUFU.EX2).
+struct LapK { pk::f2 sc2; float dcap; };
 template <bool FM>
-__device__ __forceinline__ pk::f2 lap2(float da, float db, pk::f2 sc2) {
-    const pk::f2 d = pk::mul2(pk::pack(da, db), sc2);
-    if constexpr (FM) { float a, b; pk::unpack(d, a, b); return pk::pack(pk::ex2_approx(a), pk::ex2_approx(b)); }
-    else return pk::exp2_nonpos(-pk::lo(d), -pk::hi(d));
+__device__ __forceinline__ LapK lap_k(float sigma) {
+    LapK k;
+    if constexpr (FM) { const float rinv = 1.0f / sigma; k.sc2 = pk::dup(-rinv * 1.44269504088896341f); k.dcap = 0.0f; }
+    else { const dm::LapScale L = dm::lap_scale(sigma); k.sc2 = pk::dup(L.ns2); k.dcap = L.dcap; }
+    return k;
 }
-
-// the same from already scaled arguments xa = da * sc, xb = db * sc (each the rounded product lap2 forms)
+namespace pk {
+// two dm::lap_ at once.  The clamp is a scalar instruction whose destination is free, so it drops each distance straight into the register pair the packed
+// polynomial works on; the 2^n scaling stays a float multiply (a NaN distance or bandwidth stays a NaN).
+__device__ __forceinline__ f2 lap2_exact(float da, float db, f2 ns2, float dcap) {
+    const float MAGIC = 12582912.0f;
+    float sa, sb;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(sa) : "f"(da), "f"(dcap));
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(sb) : "f"(db), "f"(dcap));
+    const f2 dc = pack(sa, sb);
+    const f2 t = fma2(dc, ns2, dup(MAGIC));
+    const f2 f = fma2(dc, ns2, fma2(t, dup(-1.0f), dup(MAGIC)));          // MAGIC - t is exact
+    f2 p = dup(DM_LAP_C6);
+    p = fma2(p, f, dup(DM_LAP_C5)); p = fma2(p, f, dup(DM_LAP_C4)); p = fma2(p, f, dup(DM_LAP_C3));
+    p = fma2(p, f, dup(DM_LAP_C2)); p = fma2(p, f, dup(DM_LAP_C1)); p = fma2(p, f, dup(1.0f));
+    float ta, tb; unpack(t, ta, tb);
+    // bits(t) = bits(MAGIC) + n and bits(MAGIC) << 23 == 0 (mod 2^32)  =>  (bits(t) << 23) + 0x3f800000 = bits(2^n)
+    const float sca = dm::u2f((dm::f2u(ta) << 23) + 0x3f800000u), scb = dm::u2f((dm::f2u(tb) << 23) + 0x3f800000u);
+    return mul2(p, pack(sca, scb));
+}
+}  // namespace pk
 template <bool FM>
-__device__ __forceinline__ pk::f2 lap2s(float xa, float xb) {
-    if constexpr (FM) return pk::pack(pk::ex2_approx(xa), pk::ex2_approx(xb));
-    else return pk::exp2_nonpos(-xa, -xb);
+__device__ __forceinline__ pk::f2 lap2(float da, float db, const LapK& k) {
+    if constexpr (FM) { float a, b; pk::unpack(pk::mul2(pk::pack(da, db), k.sc2), a, b); return pk::pack(pk::ex2_approx(a), pk::ex2_approx(b)); }
+    else return pk::lap2_exact(da, db, k.sc2, k.dcap);
 }
 
 #define ICF_THREADS 96
@@ -138,10 +134,8 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
     constexpr int nm = NR * NR;
     constexpr bool VEC = (LDD % 4 == 0) && nm >= 4;
     constexpr int MV = VEC ? (nm & ~3) : 0;          // columns handled by the vectorised loop
-    const float rinv = 1.0f / sigma;
-    const float sc = FM ? -rinv * 1.44269504088896341f : rinv;
-    const pk::f2 rinv2 = pk::dup(sc);
-    // ---- ker_mixed row sums: rowsum_i = sum_m exp(-(D[idx_i][m] * rinv)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]
+    const LapK rinv2 = lap_k<FM>(sigma);
+    // ---- ker_mixed row sums: rowsum_i = sum_m k(D[idx_i][m]; sigma), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]
     constexpr int NP = NR / 2;                       // pairs of reduced rows handled together
     pk::f2 rs2[NP > 0 ? NP : 1];
     float rsl = 0.0f;                                // last row when NR is odd
@@ -151,25 +145,20 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
 #pragma unroll
     for (int i = 0; i < NR; i++) Dr[i] = D + ti[i] * LDD;       // D is symmetric bit for bit: row idx_i
     if constexpr (VEC) {
-        // The scaling d * (1/sigma) runs on the register pairs the 16-byte loads deliver (columns m, m+1 of ONE row); the clamp of the exponential's argument is a
-        // scalar instruction whose destination is free, so it drops each value into the (row 2p, row 2p+1) pair the packed polynomial works on -- no register moves.
         // Addresses: one loop-carried register (table base + 4 m) and one multiply-add per row and trip, instead of an index and a scaled add per row.
-        uint32_t dm = pk::smem_addr(D);
+        uint32_t dmo = pk::smem_addr(D);
 #pragma unroll 1
-        for (int m = 0; m < MV; m += 4, dm += 16) {
+        for (int m = 0; m < MV; m += 4, dmo += 16) {
 #pragma unroll
             for (int p = 0; p < NP; p++) {
-                const float4 va = pk::lds128(dm + (uint32_t)ti[2 * p] * (LDD * 4)), vb = pk::lds128(dm + (uint32_t)ti[2 * p + 1] * (LDD * 4));
-                float ax, ay, az, aw, bx, by, bz, bw;
-                pk::unpack(pk::mul2(pk::pack(va.x, va.y), rinv2), ax, ay); pk::unpack(pk::mul2(pk::pack(va.z, va.w), rinv2), az, aw);
-                pk::unpack(pk::mul2(pk::pack(vb.x, vb.y), rinv2), bx, by); pk::unpack(pk::mul2(pk::pack(vb.z, vb.w), rinv2), bz, bw);
-                rs2[p] = pk::add2(rs2[p], lap2s<FM>(ax, bx));
-                rs2[p] = pk::add2(rs2[p], lap2s<FM>(ay, by));
-                rs2[p] = pk::add2(rs2[p], lap2s<FM>(az, bz));
-                rs2[p] = pk::add2(rs2[p], lap2s<FM>(aw, bw));
+                const float4 va = pk::lds128(dmo + (uint32_t)ti[2 * p] * (LDD * 4)), vb = pk::lds128(dmo + (uint32_t)ti[2 * p + 1] * (LDD * 4));
+                rs2[p] = pk::add2(rs2[p], lap2<FM>(va.x, vb.x, rinv2));
+                rs2[p] = pk::add2(rs2[p], lap2<FM>(va.y, vb.y, rinv2));
+                rs2[p] = pk::add2(rs2[p], lap2<FM>(va.z, vb.z, rinv2));
+                rs2[p] = pk::add2(rs2[p], lap2<FM>(va.w, vb.w, rinv2));
             }
             if constexpr (NR & 1) {
-                const float4 vc = pk::lds128(dm + (uint32_t)ti[NR - 1] * (LDD * 4));
+                const float4 vc = pk::lds128(dmo + (uint32_t)ti[NR - 1] * (LDD * 4));
                 pk::f2 e = lap2<FM>(vc.x, vc.y, rinv2);
                 rsl = rsl + pk::lo(e); rsl = rsl + pk::hi(e);
                 e = lap2<FM>(vc.z, vc.w, rinv2);
@@ -199,7 +188,7 @@ __device__ __forceinline__ float beta_eval(const DCfg& c, const int (&ti)[NR], f
 #pragma unroll
     for (int p = 0; p < NP; p++) pk::unpack(rs2[p], rowsum[2 * p], rowsum[2 * p + 1]);
     if constexpr (NR & 1) rowsum[NR - 1] = rsl;
-    // ---- ker_red (symmetric bit for bit); diagonal exp(-(0 * rinv)) = 1
+    // ---- ker_red (symmetric bit for bit); diagonal k(0) = 1
     float K[NR][NR];
     {
         constexpr int NE = NR * (NR - 1) / 2;
@@ -812,11 +801,11 @@ __device__ __forceinline__ int icl_topk(const float* __restrict__ row) {
     if (near) packed = top_abs_exact<NR>(row);
     return packed;
 }
-// sum_m exp(-(D[row][m] * rinv)), m ascending, two exponentials per packed evaluation: one lane of beta_eval's row-sum loop
+// sum_m k(D[row][m]; sigma), m ascending, two kernel entries per packed evaluation: one lane of beta_eval's row-sum loop
 template <int NR>
-__device__ __forceinline__ float icl_rowsum(const float* __restrict__ Drow, float rinv) {
+__device__ __forceinline__ float icl_rowsum(const float* __restrict__ Drow, float sigma) {
     constexpr int nm = NR * NR;
-    const pk::f2 rinv2 = pk::dup(rinv);
+    const LapK rinv2 = lap_k<false>(sigma);
     float rs = 0.0f;
 #pragma unroll 4
     for (int m = 0; m + 1 < nm; m += 2) {
@@ -831,8 +820,7 @@ template <int NR, int LDD = NR * NR>
 __device__ __forceinline__ float icl_finish(const DCfg& c, int packed, float sigma, const float* __restrict__ rowsum, const float* __restrict__ D,
                                             float* __restrict__ beta_out) {
     constexpr int nm = NR * NR;
-    const float rinv = 1.0f / sigma;
-    const pk::f2 rinv2 = pk::dup(rinv);
+    const LapK rinv2 = lap_k<false>(sigma);
     int ti[NR];
 #pragma unroll
     for (int i = 0; i < NR; i++) ti[i] = (packed >> (5 * i)) & 31;
@@ -1067,8 +1055,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
 #pragma unroll 1
         for (int task = tid; task < n_new * NR; task += nt) {
             const int s = task / NR, i = task - s * NR;
-            const float rinv = 1.0f / rows[s * rstride + nm];
-            rsum[task] = icl_rowsum<NR>(D + ((tis[s] >> (5 * i)) & 31) * LDD, rinv);
+            rsum[task] = icl_rowsum<NR>(D + ((tis[s] >> (5 * i)) & 31) * LDD, rows[s * rstride + nm]);
         }
         __syncthreads();
 #pragma unroll 1

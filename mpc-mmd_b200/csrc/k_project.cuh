@@ -71,6 +71,7 @@ __global__ void k_math_vec(int fn, const float* x, const float* y, float* out, i
             case 9: v = dm::exp_nonpos(x[i]); break;
             case 10: { float s, cc; dm::sincos_(x[i], s, cc); v = s; } break;
             case 11: { float s, cc; dm::sincos_(x[i], s, cc); v = cc; } break;
+            case 12: v = dm::lap_(x[i], dm::lap_scale(y[i])); break;          // Laplace kernel entry k(d = x; sigma = y) of the reduced-set inner CEM
             default: v = DM_NAN;
         }
         out[i] = v;

@@ -500,23 +500,23 @@ __device__ __forceinline__ void beta_topk(const float* __restrict__ row, int* __
 }
 // sum_m exp(-(D[m][ti] / sigma)), ascending m  [kernel_computation.py:31-37, compute_beta.py:77]; D is symmetric bit for bit
 __device__ __forceinline__ float beta_rowsum(const float* __restrict__ D, int nm, int ti, float sigma) {
-    const float rinv = 1.0f / sigma;
+    const dm::LapScale ls = dm::lap_scale(sigma);
     float acc = 0.0f;
 #pragma unroll 4
-    for (int m = 0; m < nm; m++) acc = acc + dm::exp_nonpos(-(D[m * nm + ti] * rinv));
+    for (int m = 0; m < nm; m++) acc = acc + dm::lap_(D[m * nm + ti], ls);
     return acc;
 }
 template <int NR>
 __device__ __forceinline__ float beta_finish(const DCfg& c, const int* __restrict__ ti, float sigma, const float* __restrict__ rowsum,
                                              const float* __restrict__ D, float* __restrict__ beta_out) {
     constexpr int nm = NR * NR;
-    const float rinv = 1.0f / sigma;
-    float K[NR][NR];                               // ker_red (symmetric bit for bit); diagonal: exp(-(0 * rinv)) = 1
+    const dm::LapScale ls = dm::lap_scale(sigma);
+    float K[NR][NR];                               // ker_red (symmetric bit for bit); diagonal: k(0) = 1
 #pragma unroll
     for (int i = 0; i < NR; i++) {
         K[i][i] = 1.0f;
 #pragma unroll
-        for (int j = 0; j < i; j++) { const float k = dm::exp_nonpos(-(D[ti[i] * nm + ti[j]] * rinv)); K[i][j] = k; K[j][i] = k; }
+        for (int j = 0; j < i; j++) { const float k = dm::lap_(D[ti[i] * nm + ti[j]], ls); K[i][j] = k; K[j][i] = k; }
     }
     // A = ker_red + 0.05 I, Cholesky with reciprocal pivots
     float Lm[NR][NR], rd[NR], u[NR], w[NR];
@@ -577,7 +577,7 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restr
     int ti[NR];
     beta_topk<NR>(row, ti);
     const float sigma = row[nm];
-    const float rinv = 1.0f / sigma;
+    const dm::LapScale ls = dm::lap_scale(sigma);
     float rowsum[NR];
 #pragma unroll
     for (int i = 0; i < NR; i++) rowsum[i] = 0.0f;
@@ -585,7 +585,7 @@ __device__ __forceinline__ float beta_sample(const DCfg& c, const float* __restr
     for (int m = 0; m < nm; m++) {                 // D is symmetric bit for bit: read column m (bank-conflict free across threads)
         const float* Dm = D + m * nm;
 #pragma unroll
-        for (int i = 0; i < NR; i++) rowsum[i] = rowsum[i] + dm::exp_nonpos(-(Dm[ti[i]] * rinv));
+        for (int i = 0; i < NR; i++) rowsum[i] = rowsum[i] + dm::lap_(Dm[ti[i]], ls);
     }
 #pragma unroll
     for (int i = 0; i < NR; i++) idx_out[i] = ti[i];

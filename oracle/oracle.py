@@ -152,7 +152,7 @@ def threefry(k0, k1, x0, x1):
     return int(o[0]), int(o[1])
 
 
-MATH_FN = {"exp": 0, "log": 1, "log1p": 2, "sin": 3, "cos": 4, "tan": 5, "atan": 6, "atan2": 7, "erfinv": 8}
+MATH_FN = {"exp": 0, "log": 1, "log1p": 2, "sin": 3, "cos": 4, "tan": 5, "atan": 6, "atan2": 7, "erfinv": 8, "lap": 12}
 
 
 def math_vec(fn, x, y=None):

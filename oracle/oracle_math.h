@@ -43,6 +43,33 @@ static inline float om_exp(float x) {
     return y * om_u2f((uint32_t)(n + 127) << 23);
 }
 
+/* Laplace kernel entry k(d; sigma) = 2^(-(d * s2)) of the reduced-set inner CEM (the contract's form of exp(-d / sigma), kernel_computation.py:31-37;
+ * DESIGN.md section 3, D1 -- restated, csrc/dmath.cuh dm::lap_ is the same operations):
+ *   per bandwidth: rinv = 1 / sigma, s2 = rinv * log2(e), dcap = 125 / s2;
+ *   per distance:  dc = min(d, dcap) (NaN propagates), t = fma(dc, -s2, MAGIC), n = bits(t) - bits(MAGIC), f = fma(dc, -s2, MAGIC - t) in [-1/2, 1/2],
+ *                  p = P6(f) ~ 2^f (degree-6 minimax, constant term 1), k = p * 2^n.  <= 1 ulp of 2^(-(d s2)); k(0) = 1 exactly. */
+typedef struct { float ns2, dcap; } om_lapscale_t;
+static inline om_lapscale_t om_lap_scale(float sigma) {
+    float rinv = 1.0f / sigma;
+    float s2 = rinv * 1.44269504088896341f;
+    om_lapscale_t L; L.ns2 = -s2; L.dcap = 125.0f / s2;
+    return L;
+}
+static inline float om_lap(float d, om_lapscale_t L) {
+    const float MAGIC = 12582912.0f;
+    float dc = (d != d || L.dcap != L.dcap) ? NAN : (d < L.dcap ? d : L.dcap);      /* min.NaN.f32 */
+    float t = fmaf(dc, L.ns2, MAGIC);
+    float f = fmaf(dc, L.ns2, MAGIC - t);
+    float p = 0.00015469731971976444f;
+    p = fmaf(p, f, 0.0013410000965866657f);
+    p = fmaf(p, f, 0.009618030782528724f);
+    p = fmaf(p, f, 0.05550297314200181f);
+    p = fmaf(p, f, 0.24022651084117067f);
+    p = fmaf(p, f, 0.6931472253950105f);
+    p = fmaf(p, f, 1.0f);
+    return p * om_u2f((om_f2u(t) << 23) + 0x3f800000u);
+}
+
 /* log(x): x<0 -> NaN, 0 -> -inf, inf -> inf, denormals handled by pre-scaling. */
 static inline float om_log(float x) {
     if (x != x) return x;

@@ -514,12 +514,12 @@ void oracle_inner_cem(const ocfg_t *c, const float *F /* (nm,22) */, oinner_out_
             int *idx = idxs + s * nr;
             float sigma = row[nm], rowsum[64];
             top_abs(row, nm, nr, idx);
-            float rinv = 1.0f / sigma;                                           /* [D1] */
+            om_lapscale_t ls = om_lap_scale(sigma);                              /* [D1] */
             for (int i = 0; i < nr; i++) {
                 float rs = 0.0f;
                 for (int m = 0; m < nm; m++) {
                     float dist = c->naive ? l1_dist(F + idx[i] * 2 * NV, F + m * 2 * NV) : D[idx[i] * nm + m];
-                    float k = om_exp(-(dist * rinv));
+                    float k = om_lap(dist, ls);
                     Kmix[i * nm + m] = k;
                     rs = rs + k;
                 }
@@ -527,7 +527,7 @@ void oracle_inner_cem(const ocfg_t *c, const float *F /* (nm,22) */, oinner_out_
             }
             for (int i = 0; i < nr; i++)
                 for (int j = 0; j < nr; j++) {
-                    if (c->naive) { float dist = l1_dist(F + idx[i] * 2 * NV, F + idx[j] * 2 * NV); Kred[i * nr + j] = om_exp(-(dist * rinv)); }
+                    if (c->naive) { float dist = l1_dist(F + idx[i] * 2 * NV, F + idx[j] * 2 * NV); Kred[i * nr + j] = om_lap(dist, ls); }
                     else Kred[i * nr + j] = Kmix[i * nm + idx[j]];
                 }
             cost[s] = beta_qp(c, Kred, rowsum, betas + s * nr);
@@ -842,6 +842,7 @@ void oracle_math_vec(int fn, const float *x, const float *y, float *out, int n) 
             case 6: out[i] = om_atan(x[i]); break;
             case 7: out[i] = om_atan2(y[i], x[i]); break;
             case 8: out[i] = xla_erfinv32(x[i]); break;
+            case 12: out[i] = om_lap(x[i], om_lap_scale(y[i])); break;          /* Laplace kernel entry k(d = x; sigma = y) */
             default: out[i] = NAN;
         }
     }

@@ -76,6 +76,26 @@ def test_oracle_math_accuracy(O, fn, lo, hi, ref, tol):
     assert _ulps(O.math_vec(fn, x), ref(x.astype(np.float64))).max() <= tol
 
 
+def test_oracle_laplace_kernel_entry_accuracy(O):
+    """k(d; sigma) of the reduced-set inner CEM (contract form of exp(-d / sigma), kernel_computation.py:31-37): within 1.5 ulp of 2^(-(d * s2)) for the contract's
+    own float32 s2, within 2e-6 relative of exp(-d / sigma) in float64 over the working range (s2's two roundings times |d / sigma| <= 16), k(0) = 1 exactly,
+    the distance cap keeps huge d / sigma at 2^-125, NaN distance or bandwidth gives NaN."""
+    rng = np.random.default_rng(3)
+    d = np.concatenate([rng.uniform(0, 40, 300000), rng.uniform(0, 1e-3, 1000)]).astype(f32)
+    sig = rng.uniform(0.01, 5.0, d.size).astype(f32)
+    k = O.math_vec("lap", d, sig)
+    s2 = ((f32(1.0) / sig).astype(f32) * f32(1.44269504088896341)).astype(f32)
+    cap = (f32(125.0) / s2).astype(f32)
+    ref = np.exp2(-(np.minimum(d, cap).astype(np.float64) * s2.astype(np.float64)))
+    assert _ulps(k, ref).max() <= 1.5
+    m = d.astype(np.float64) / sig <= 16.0
+    assert np.max(np.abs(k[m] / np.exp(-(d[m].astype(np.float64) / sig[m].astype(np.float64))) - 1.0)) < 2e-6
+    assert np.all(O.math_vec("lap", np.zeros(5, f32), np.array([0.01, 0.3, 1.0, 7.0, 1e9], f32)) == 1.0)
+    big = O.math_vec("lap", np.array([1e6, np.inf], f32), np.array([0.01, 0.01], f32))
+    assert np.all(big > 0) and np.all(big <= f32(2.0) ** -124)
+    assert np.isnan(O.math_vec("lap", np.array([np.nan, 1.0], f32), np.array([1.0, np.nan], f32))).all()
+
+
 def test_oracle_math_special_values(O):
     assert O.math_vec("exp", np.array([-1000.0], f32))[0] == O.math_vec("exp", np.array([-87.0], f32))[0] > 0      # clamp, part of the contract
     assert np.isneginf(O.math_vec("log", np.array([0.0], f32))[0]) and np.isnan(O.math_vec("log", np.array([-1.0], f32))[0])

@@ -39,6 +39,15 @@ def test_ieee_shortcuts_exhaustive(mods):
     assert cem_impl.selfcheck_ieee(0) == (0, 0, 0)
 
 
+def test_device_laplace_kernel_entry_bit_exact(mods):
+    """dm::lap_ (csrc/dmath.cuh) == om_lap (oracle/oracle_math.h): the Laplace kernel entry of the reduced-set inner CEM, including capped, zero, infinite and NaN arguments"""
+    cem_impl, O = mods
+    rng = np.random.default_rng(5)
+    d = np.concatenate([rng.uniform(0, 60, 400000), rng.uniform(0, 1e4, 100000), [0.0, -0.0, np.inf, np.nan, 1.0, 1.0, 3.0]]).astype(f32)
+    sig = np.concatenate([rng.uniform(0.01, 4.0, 500000), [1.0, 1.0, 0.01, 1.0, np.nan, np.inf, 0.0]]).astype(f32)
+    _eq(cem_impl.math_vec(12, d, sig), O.math_vec("lap", d, sig), "lap")
+
+
 @pytest.mark.parametrize("fn", list(MATH_RANGES))
 def test_device_math_bit_exact(mods, fn):
     cem_impl, O = mods
