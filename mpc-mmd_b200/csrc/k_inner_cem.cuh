@@ -454,6 +454,83 @@ __device__ __forceinline__ void icf_chol_panel(float* __restrict__ C, int ldc_, 
     }
 }
 
+// Cholesky of the d x d covariance by the WHOLE CTA (3 warps), left-looking by panels of four columns, same per-entry operation order as icf_chol_panel (so the
+// same bits): entry (r, j) accumulates fma(-L_rk, L_jk, .) for k ascending, then the pivot's square root / reciprocal scaling.  The one-warp version leaves two of the
+// three warps parked behind a barrier for a third of the kernel's time; here
+//   A. every thread owns ONE entry (row r >= j0, column j0 + u) of the panel and runs its k < j0 chain (2 shared loads + 1 fma per k), result to a scratch S[r][u];
+//   B. warp 0 factors the 4 x 4 diagonal block from S (the serial sqrt -> reciprocal chain, once per CTA) and publishes pivots, reciprocals and the six
+//      sub-diagonal entries in F;
+//   C. every thread finishes its entry with the block's columns, stores it into the transposed factor (LT[k][q] = L[q][k], upper triangle of C) and zeroes the
+//      consumed covariance entry below the diagonal (the zero fill the resampling relies on).
+// Three block barriers per panel.  S (d x 4 floats) and F (16 floats) live in a region that is dead during the factorisation.
+template <int d>
+__device__ __forceinline__ void icf_chol_cta(float* __restrict__ C, float* __restrict__ scratch, int tid) {
+    constexpr int NG = (d + 3) / 4, ldc = (d + 3) & ~3, RPP = ICF_THREADS / 4;       // rows per pass
+    float* S = scratch; float* F = scratch + 4 * ((d + 3) & ~3);
+    const int u = tid & 3, ro = tid >> 2, warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+    for (int p = 0; p < NG; p++) {
+        const int j0 = 4 * p;
+        // ---- A: k < j0 part of every panel entry (rows below j0 are final already)
+#pragma unroll 1
+        for (int r = j0 + ro; r < d; r += RPP) {
+            float acc = C[r * ldc + j0 + u];
+            const float* pr = C + r; const float* pj = C + j0 + u;
+#pragma unroll 1
+            for (int k4 = 0; k4 < p; k4++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc = fmaf(-pr[q * ldc], pj[q * ldc], acc);
+                pr += 4 * ldc; pj += 4 * ldc;
+            }
+            S[r * 4 + u] = acc;
+        }
+        __syncthreads();
+        // ---- B: the diagonal block (rows beyond the matrix shadow the last row, as the lanes of icf_chol_panel do; their results are never stored)
+        if (warp == 0) {
+            const float4 b0 = *reinterpret_cast<const float4*>(S + 4 * j0);
+            const float4 b1 = *reinterpret_cast<const float4*>(S + 4 * (j0 + 1 < d ? j0 + 1 : d - 1));
+            const float4 b2 = *reinterpret_cast<const float4*>(S + 4 * (j0 + 2 < d ? j0 + 2 : d - 1));
+            const float4 b3 = *reinterpret_cast<const float4*>(S + 4 * (j0 + 3 < d ? j0 + 3 : d - 1));
+            float d0, r0, d1, r1, d2, r2, d3, r3;
+            dm::sqrt_rcp(b0.x, d0, r0);
+            const float l10 = b1.x * r0, l20 = b2.x * r0, l30 = b3.x * r0;
+            dm::sqrt_rcp(fmaf(-l10, l10, b1.y), d1, r1);
+            const float l21 = fmaf(-l20, l10, b2.y) * r1, l31 = fmaf(-l30, l10, b3.y) * r1;
+            dm::sqrt_rcp(fmaf(-l21, l21, fmaf(-l20, l20, b2.z)), d2, r2);
+            const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, b3.z)) * r2;
+            dm::sqrt_rcp(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, b3.w))), d3, r3);
+            if (lane == 0) {
+                *reinterpret_cast<float4*>(F) = make_float4(d0, d1, d2, d3);
+                *reinterpret_cast<float4*>(F + 4) = make_float4(r0, r1, r2, r3);
+                *reinterpret_cast<float4*>(F + 8) = make_float4(l10, l20, l30, l21);
+                *reinterpret_cast<float4*>(F + 12) = make_float4(l31, l32, 0.0f, 0.0f);
+            }
+        }
+        __syncthreads();
+        // ---- C: own entry L[r][j0 + u] (on the diagonal the pivot itself), transposed store, zero fill
+        {
+            const float4 dg = *reinterpret_cast<const float4*>(F), rc = *reinterpret_cast<const float4*>(F + 4);
+            const float4 la = *reinterpret_cast<const float4*>(F + 8), lb = *reinterpret_cast<const float4*>(F + 12);
+            const float l10 = la.x, l20 = la.y, l30 = la.z, l21 = la.w, l31 = lb.x, l32 = lb.y;
+            const int col = j0 + u;
+#pragma unroll 1
+            for (int r = j0 + ro; r < d; r += RPP) {
+                const float4 a = *reinterpret_cast<const float4*>(S + 4 * r);
+                const float e0 = a.x * rc.x;
+                const float e1 = fmaf(-e0, l10, a.y) * rc.y;
+                const float e2 = fmaf(-e1, l21, fmaf(-e0, l20, a.z)) * rc.z;
+                const float e3 = fmaf(-e2, l32, fmaf(-e1, l31, fmaf(-e0, l30, a.w))) * rc.w;
+                float val = u == 0 ? e0 : u == 1 ? e1 : u == 2 ? e2 : e3;
+                const float dv = u == 0 ? dg.x : u == 1 ? dg.y : u == 2 ? dg.z : dg.w;
+                if (r == col) val = dv;
+                if (col < d && r >= col) C[col * ldc + r] = val;
+                if (col < d && r > col) C[r * ldc + col] = 0.0f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // one covariance task: C[r][4*q4 .. 4*q4+3] = (sum_el xc[el][r] * xc[el][q]) / (ne - 1) (+ 0.05 on the diagonal), el ascending  [compute_beta.py:61]
 __device__ __forceinline__ void icf_cov_task(const float* __restrict__ xc, float* __restrict__ C, int ldc, int ne, int r, int q4) {
     const float nm1 = (float)(ne - 1);
@@ -550,8 +627,9 @@ template <int d> __device__ __forceinline__ void icl_chol_lookahead(float* __res
 // FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
 // SC / NEC = compile-time copies of the inner CEM's sample / elite counts (0 = read them from the configuration): with the reference's sizes (100 / 11) baked in, the
 // whole shared-memory layout folds into immediate offsets, which takes the address arithmetic the 56-register cap otherwise re-derives in every phase out of the kernel
-// LA = two-warp look-ahead Cholesky (icl_chol_lookahead) instead of the one-warp panel factorisation (MPCMMD_CHOL=la, measured variant)
-template <int NR, bool LAT, bool FM = false, int SC = 0, int NEC = 0, bool LA = false>
+// CH = Cholesky of the covariance: 0 one-warp panel factorisation (icf_chol_panel), 1 two-warp look-ahead (icl_chol_lookahead), 2 CTA-wide panels (icf_chol_cta);
+// MPCMMD_CHOL=panel|la|cta selects the build of the specialised throughput kernel
+template <int NR, bool LAT, bool FM = false, int SC = 0, int NEC = 0, int CH = 0>
 __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -668,7 +746,8 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel).  The two-warp look-ahead variant of the
         //    latency kernel (icl_chol_lookahead, partial sums in the dead row region) was measured here too (-DICF_CHOL_LOOKAHEAD): 155.7 vs 153.6 ms per 200-episode
         //    solve -- under the 56-register cap it spills, and with 12 chains per SM the phase is bound by issued instructions, not by warp 0's critical path.
-        if constexpr (LA) { if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane); }
+        if constexpr (CH == 1) { if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane); }
+        else if constexpr (CH == 2) icf_chol_cta<d>(C, xc, tid);
         else if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
         __syncthreads();
         // -- resample: one thread per new row, two columns per packed accumulator, k ascending  [compute_beta.py:63-66].

@@ -209,13 +209,14 @@ static SplitKernels split_kernels(int nr) {
 }
 static size_t split_eval_smem(const DCfg& d) { const int dd = d.nm + 1; return (size_t)(al4(d.nm * d.nm) + (dd + 1) * al4(dd)) * sizeof(float); }
 static size_t split_update_smem(const DCfg& d) { return (size_t)ICU_WARPS * upd_layout(d.nr).total * sizeof(float); }
-static bool g_chol_la = false;       // MPCMMD_CHOL=la (read at create): look-ahead Cholesky build of the specialised throughput kernel
+static int g_chol = 0;       // MPCMMD_CHOL=panel|la|cta (read at create): Cholesky build of the specialised throughput kernel (0 one-warp panels, 1 two-warp look-ahead, 2 CTA-wide panels)
 static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_WARP) switch (d.nr) {
         case 2: return k_inner_cem_warp<2>; case 3: return k_inner_cem_warp<3>; case 4: return k_inner_cem_warp<4>; case 5: return k_inner_cem_warp<5>;
     }
     if (d.nr == 5 && d.S_in == 100 && d.n_el_in == 11) {          // the reference's sizes as compile-time constants
-        if (kind == INNER_CTA && g_chol_la) return k_inner_cem_fast<5, false, false, 100, 11, true>;
+        if (kind == INNER_CTA && g_chol == 1) return k_inner_cem_fast<5, false, false, 100, 11, 1>;
+        if (kind == INNER_CTA && g_chol == 2) return k_inner_cem_fast<5, false, false, 100, 11, 2>;
         if (kind == INNER_CTA) return k_inner_cem_fast<5, false, false, 100, 11>;
         if (kind == INNER_CTA_LAT) return k_inner_cem_fast<5, true, false, 100, 11>;
         if (kind == INNER_CTA_FASTMATH) return k_inner_cem_fast<5, false, true, 100, 11>;
@@ -420,7 +421,7 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
             if (raise_smem(device, (const void*)pipe_kernel(d.nr, h->pipe_minb), pipe_smem_bytes(d.nr, d.S_in, d.n_el_in), true)) return fail("k_inner_cem_pipe smem opt-in failed");
         }
         { const char* mm = getenv("MPCMMD_MATH"); h->fast_math = mm && !strcmp(mm, "fast"); }
-        { const char* cl = getenv("MPCMMD_CHOL"); g_chol_la = cl && !strcmp(cl, "la"); }
+        { const char* cl = getenv("MPCMMD_CHOL"); g_chol = !cl ? 0 : !strcmp(cl, "la") ? 1 : !strcmp(cl, "cta") ? 2 : 0; }
         for (int kind = INNER_WARP; kind <= INNER_LAT512; kind++) {
             if (kind == INNER_SPLIT || kind == INNER_PIPE || kind == INNER_BIG) continue;
             if (kind != INNER_GENERIC && !inner_cem_is_fast(d)) continue;
