@@ -138,7 +138,8 @@ int mpcmmd_selfcheck_ieee(int device, unsigned long long *mismatches /* [3], hos
 
 /* ---- stage entry points (teacher-forced parity tests; all DEVICE pointers, synchronous) ---- */
 
-/* deterministic math / RNG primitives: fn 0 exp,1 log,2 log1p,3 sin,4 cos,5 tan,6 atan,7 atan2(y,x),8 erfinv */
+/* deterministic math / RNG primitives: fn 0 exp,1 log,2 log1p,3 sin,4 cos,5 tan,6 atan,7 atan2(y,x),8 erfinv, 9 exp on x <= 0, 10/11 sincos,
+ * 12 Laplace kernel entry k(d = x; sigma = y) = 2^(-(d s2)) of the reduced-set inner CEM (kernel_computation.py:31-37) */
 int mpcmmd_math_vec(int fn, const float *x, const float *y, float *out, int n, int device);
 int mpcmmd_rng_normal(uint32_t k0, uint32_t k1, int n, float *out, int device);
 int mpcmmd_rng_beta(uint32_t k0, uint32_t k1, const float *a, const float *b, int n, float *out, int device);

@@ -690,6 +690,26 @@ def test_full_sweep_is_batch_invariant(mods):
         _eq(out["cx"][k], ref["cx"], f"episode {k} cx vs oracle"); _eq(out["cost_obs"][k], ref["cost_obs"], f"episode {k} cost_obs vs oracle")
 
 
+@pytest.mark.parametrize("E,groups", [(13, None), (25, None), (25, "5"), (7, "8")])
+def test_solve_graph_episode_groups_are_invariant(mods, monkeypatch, E, groups):
+    """strong-scaled shards: an mmd_opt solve of 13 / 25 episodes is captured as 2 / 3 episode groups on parallel graph branches (solve_groups; MPCMMD_GROUPS forces
+    other counts, capped by the episode count: ragged groups, more groups than the automatic rule ever picks).  Every episode equals the same episode solved alone."""
+    cem_impl, _ = mods
+    from mpcmmd_b200 import scenes
+    if groups:
+        monkeypatch.setenv("MPCMMD_GROUPS", groups)
+    args = (5, 4, 0.3, 50, "beta", 0.0, 0.0)
+    big = cem_impl.CEM(*args, variant="static", max_episodes=E)
+    monkeypatch.delenv("MPCMMD_GROUPS", raising=False)
+    one = cem_impl.CEM(*args, variant="static", max_episodes=1)
+    batch = scenes.static_batch(big, list(range(E)))
+    out = big.solve_batch("mmd_opt", **batch)
+    for k in sorted({0, E // 3, E // 2, (2 * E) // 3, E - 1}):
+        solo = one.solve_batch("mmd_opt", **{n: v[k:k + 1] for n, v in batch.items()})
+        for f in ("cx", "cy", "cost_obs", "cost_lane", "beta", "sigma", "res_beta"):
+            _eq(out[f][k], solo[f][0], f"E={E} groups={groups} episode {k} {f}: grouped graph vs alone")
+
+
 def test_full_sweep_matches_oracle_episode_by_episode(mods):
     """BASELINE configs[1] at full size: ALL 200 episodes of the cvar sweep and 12 episodes of the mmd_opt sweep, solved in one batch each,
     against the oracle episode by episode -- trajectories, costs, and the accepted set that main_mpc.py would write (cost_obs <= threshold)."""
