@@ -887,12 +887,28 @@ __device__ __forceinline__ int icl_topk(const float* __restrict__ row) {
     int tk[NR + 1];
 #pragma unroll
     for (int p = 0; p <= NR; p++) tk[p] = 0;
-#pragma unroll
-    for (int m = 0; m < nm; m++) {
-        int v = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m);
+    auto insert = [&](float x, int m) {
+        const int v = (int)((dm::f2u(x) & 0x7fffffe0u) | (uint32_t)m);
         tk[0] = max(tk[0], v);
 #pragma unroll
         for (int p = 0; p < NR; p++) { const int lo = min(tk[p], tk[p + 1]), hi = max(tk[p], tk[p + 1]); tk[p] = lo; tk[p + 1] = hi; }
+    };
+    if constexpr (NR == 5) {                       // the merge network of beta_sample_fast, unrolled (one chain per SM: code size is no concern here)
+#define ICF_CE(a, b) { const int lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+#pragma unroll
+        for (int m = 0; m + 3 < nm; m += 4) {
+            int s0 = (int)((dm::f2u(row[m]) & 0x7fffffe0u) | (uint32_t)m), s1 = (int)((dm::f2u(row[m + 1]) & 0x7fffffe0u) | (uint32_t)(m + 1));
+            int s2 = (int)((dm::f2u(row[m + 2]) & 0x7fffffe0u) | (uint32_t)(m + 2)), s3 = (int)((dm::f2u(row[m + 3]) & 0x7fffffe0u) | (uint32_t)(m + 3));
+            ICF_CE(s0, s1) ICF_CE(s2, s3) ICF_CE(s0, s2) ICF_CE(s1, s3) ICF_CE(s1, s2)
+            tk[0] = max(tk[0], s3); tk[1] = max(tk[1], s2); tk[2] = max(tk[2], s1); tk[3] = max(tk[3], s0);
+            ICF_CE(tk[0], tk[4]) ICF_CE(tk[1], tk[5]) ICF_CE(tk[0], tk[2]) ICF_CE(tk[1], tk[3]) ICF_CE(tk[0], tk[1]) ICF_CE(tk[2], tk[3]) ICF_CE(tk[4], tk[5])
+        }
+#undef ICF_CE
+#pragma unroll
+        for (int m = nm & ~3; m < nm; m++) insert(row[m], m);
+    } else {
+#pragma unroll
+        for (int m = 0; m < nm; m++) insert(row[m], m);
     }
     int packed = 0; bool near = false;
 #pragma unroll

@@ -278,7 +278,11 @@ __device__ __forceinline__ void rollout_risk(const DCfg& c, const RiskArgs& A, i
 
 // MODE 0: mmd_opt; 1: num_reduced-rollout costs, throughput regime; 2: the same, latency regime.  Three instantiations keep each launch's code small.
 enum { ROLL_OPT = 0, ROLL_FLY = 1, ROLL_STAGED = 2 };
-template <int MODE, bool SORTED = false, int NZ = NZ_ANY>
+// OV (ROLL_OPT only) = which of the three mmd_opt bodies the launch runs, fixed at compile time so that the throughput kernel does not carry the other two (the
+// combined kernel was 4500 SASS instructions, instruction-fetch stalls 2.5 per issue): 0 features only, 1 also the mother rollouts' positions (generic / warp-per-chain
+// inner kernels read them back), 2 the latency regime (RollArgs::fold_risk)
+enum { OV_PLAIN = 0, OV_WRITE = 1, OV_FOLD = 2 };
+template <int MODE, bool SORTED = false, int NZ = NZ_ANY, int OV = OV_PLAIN>
 __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = tn;
         }
         __syncthreads();
-        if (ra.fold_risk) {
+        if constexpr (OV == OV_FOLD) {
             // ---- latency regime (a handful of samples per SM): the serial part of a mother rollout is reduced to the bare bicycle recurrence -- positions go to
             //      shared memory -- and everything that only READS the positions runs in parallel afterwards: one thread per (rollout, feature) for the 22
             //      ridge-fit chains (ascending t: the contract's order), one warp per rollout with a lane per knot for the obstacle / lane maxima.
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
             const int ls = i / R, m = i % R, g = g0 + ls, e = g / a.B;
             const float* an = sm + ls * 2 * n + (m / nr) * np; const float* sn = sm + ls * 2 * n + n + (m % nr) * np;
             float* ft = ra.feat + ((size_t)g * R + m) * 2 * NV;
-            if (ra.write_rolls) rollout_fit<1>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
+            if constexpr (OV == OV_WRITE) rollout_fit<1>(c, an, sn, a.state0 + e * 5, sW, ra.xroll + ((size_t)g * R + m) * np, ra.yroll + ((size_t)g * R + m) * np, ft);
             else rollout_fit<0>(c, an, sn, a.state0 + e * 5, sW, nullptr, nullptr, ft);
         }
     } else {

@@ -177,11 +177,13 @@ static size_t roll_smem(const mpcmmd_handle_s* h, int kind) {
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 // k_rollouts instantiation of a launch: mode (ROLL_*), noise path (NZ_*), sorted obstacle windows (ROLL_FLY only; Gaussian or the run-time noise path)
-static const void* rollouts_kernel(int mode, int nz, int sorted) {
-    if (mode == ROLL_OPT) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_OPT, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_OPT, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_OPT, false, NZ_ANY>;
-    if (mode == ROLL_STAGED) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_STAGED, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_STAGED, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_STAGED, false, NZ_ANY>;
+static const void* rollouts_kernel(int mode, int nz, int sorted, int ov = OV_PLAIN) {
+#define RK_NZ(M, S, O) (nz == NZ_GAUSS ? (const void*)k_rollouts<M, S, NZ_GAUSS, O> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<M, S, NZ_BETA_TABLE, O> : (const void*)k_rollouts<M, S, NZ_ANY, O>)
+    if (mode == ROLL_OPT) return ov == OV_FOLD ? RK_NZ(ROLL_OPT, false, OV_FOLD) : ov == OV_WRITE ? RK_NZ(ROLL_OPT, false, OV_WRITE) : RK_NZ(ROLL_OPT, false, OV_PLAIN);
+    if (mode == ROLL_STAGED) return RK_NZ(ROLL_STAGED, false, OV_PLAIN);
     if (sorted) return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_FLY, true, NZ_GAUSS> : (const void*)k_rollouts<ROLL_FLY, true, NZ_ANY>;
-    return nz == NZ_GAUSS ? (const void*)k_rollouts<ROLL_FLY, false, NZ_GAUSS> : nz == NZ_BETA_TABLE ? (const void*)k_rollouts<ROLL_FLY, false, NZ_BETA_TABLE> : (const void*)k_rollouts<ROLL_FLY, false, NZ_ANY>;
+    return RK_NZ(ROLL_FLY, false, OV_PLAIN);
+#undef RK_NZ
 }
 typedef void (*inner_cem_fn)(DCfg, RollArgs);
 enum { INNER_WARP = 1, INNER_CTA = 2, INNER_GENERIC = 3, INNER_CTA_LAT = 4, INNER_SPLIT = 5, INNER_PIPE = 6, INNER_CTA_FASTMATH = 7, INNER_BIG = 8, INNER_LAT512 = 9 };
@@ -401,8 +403,8 @@ static int create_body(mpcmmd_handle_s* h, const mpcmmd_config* cfg, int device)
     {
         size_t rs = nr <= MPCMMD_MAX_NR_OPT ? roll_smem(h, MPCMMD_COST_MMD_OPT) : 0; const size_t rb = roll_smem(h, MPCMMD_COST_CVAR); if (rb > rs) rs = rb;
         if (rs > 227 * 1024) return fail("mpcmmd_create: rollouts of one sample do not fit in shared memory");
-        for (int mode = 0; mode < 3; mode++) for (int nz = 0; nz < 3; nz++) for (int so = 0; so < 2; so++) {
-            const void* f = rollouts_kernel(mode, nz, so);
+        for (int mode = 0; mode < 3; mode++) for (int nz = 0; nz < 3; nz++) for (int so = 0; so < 2; so++) for (int ov = 0; ov < 3; ov++) {
+            const void* f = rollouts_kernel(mode, nz, so, ov);
             if (f && raise_smem(device, f, rs)) return fail("k_rollouts smem opt-in failed");
         }
     }
@@ -560,7 +562,7 @@ static int launch_risk(mpcmmd_handle_s* h, const RiskArgs& r, cudaStream_t s, in
         const int grid = (r.n_samples + ra.spb - 1) / ra.spb; const size_t rsm = roll_smem_for(d, r.cost_kind, ra.spb, ra.stage_ctrl, ra.fold_risk);
         const int nz = d.noise_kind == 0 ? NZ_GAUSS : (r.btab && !r.binj1) ? NZ_BETA_TABLE : NZ_ANY;
         const int mode = opt ? ROLL_OPT : ra.stage_ctrl ? ROLL_STAGED : ROLL_FLY;
-        const void* fk = rollouts_kernel(mode, nz, mode == ROLL_FLY && r.sx_obs);
+        const void* fk = rollouts_kernel(mode, nz, mode == ROLL_FLY && r.sx_obs, ra.fold_risk ? OV_FOLD : ra.write_rolls ? OV_WRITE : OV_PLAIN);
         void* kargs[] = {(void*)&d, (void*)&ra};
         CK(cudaLaunchKernel(fk, dim3(grid), dim3(ROLL_THREADS), kargs, rsm, s));
     }
