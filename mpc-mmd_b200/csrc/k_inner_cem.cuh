@@ -642,6 +642,7 @@ __device__ __forceinline__ void icf_mvn_row_regs(const float* __restrict__ LT, i
 }
 
 template <int d> __device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float* __restrict__ ps, int warp, int lane);
+template <int d> __device__ __forceinline__ void icl_chol_regs(float* __restrict__ C, int lane);
 // LAT = the build for launches that fit in a single wave of CTAs (one episode = 100 chains): no register cap (156 instead of the 56 registers
 // that let 12 chains share an SM) and the resampling normals prefetched behind the Cholesky (mmd_opt p50 at batch 1: 8.3 -> 7.4 ms)
 // FM = opt-in fast-math build (MPCMMD_MATH=fast): the Laplace-kernel exponentials on MUFU.EX2 instead of the contract's polynomial; tolerance parity only
@@ -766,7 +767,8 @@ __global__ void __launch_bounds__(ICF_THREADS, LAT ? 3 : 12) k_inner_cem_fast(DC
         // -- Cholesky by warp 0, left-looking by panels of four columns, factor transposed in place (icf_chol_panel).  The two-warp look-ahead variant of the
         //    latency kernel (icl_chol_lookahead, partial sums in the dead row region) was measured here too (-DICF_CHOL_LOOKAHEAD): 155.7 vs 153.6 ms per 200-episode
         //    solve -- under the 56-register cap it spills, and with 12 chains per SM the phase is bound by issued instructions, not by warp 0's critical path.
-        if constexpr (CH == 1) { if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane); }
+        if constexpr (LAT) { if (warp == 0) icl_chol_regs<d>(C, lane); }       // latency build: register-resident right-looking factorisation (see icl_chol_regs)
+        else if constexpr (CH == 1) { if (warp < 2) icl_chol_lookahead<d>(C, xc, warp, lane); }
         else if constexpr (CH == 2) icf_chol_cta<d>(C, xc, tid);
         else if (warp == 0) icf_chol_panel<d>(C, ldc, lane);
         __syncthreads();
@@ -1114,6 +1116,43 @@ __device__ __forceinline__ void icl_chol_lookahead(float* __restrict__ C, float*
     }
 }
 
+// Latency kernel only: Cholesky of the d x d covariance by ONE warp with the whole lower triangle in registers (lane r holds row r), right-looking and fully
+// unrolled: column j takes its pivot from lane j (one shuffle), every lane scales its entry, and the trailing entries (r, q), q > j, receive fma(-L_rj, L_qj, .)
+// with L_qj shuffled from lane q.  Entry (r, q) therefore accumulates its k terms in ascending k and is then scaled by the pivot's reciprocal: the contract's order,
+// the same bits as the panel versions.  No shared-memory round trip and no barrier inside the factorisation -- its critical path is pivot shuffle -> sqrt_rcp ->
+// scale -> one fma per column (~2.4 k cycles for d = 26 against ~7 k for the two-warp look-ahead panels); 351 shuffles and ~1.2 k instructions of straight-line code,
+// which only a kernel that has an SM to itself can afford.  The factor is written transposed with its zero fill (LT[k][q] = 0 for q < k) in one pass at the end.
+template <int d>
+__device__ __forceinline__ void icl_chol_regs(float* __restrict__ C, int lane) {
+    constexpr int NG = (d + 3) / 4, ldc = (d + 3) & ~3;
+    const int r = lane < d ? lane : d - 1;                 // lanes >= d shadow the last row (no stores)
+    float a[4 * NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const float4 v = *reinterpret_cast<const float4*>(C + r * ldc + 4 * g);
+        a[4 * g] = v.x; a[4 * g + 1] = v.y; a[4 * g + 2] = v.z; a[4 * g + 3] = v.w;
+    }
+    float piv = a[0];                                      // lane j holds the pivot of column j here when column j starts
+#pragma unroll
+    for (int j = 0; j < d; j++) {
+        const float ajj = __shfl_sync(FULL, piv, j);
+        float dd, rd; dm::sqrt_rcp(ajj, dd, rd);
+        const float l = lane == j ? dd : a[j] * rd;        // L[r][j] (meaningful for r >= j)
+        a[j] = l;
+        // the next pivot is lane j+1's own diagonal entry, whose update needs no other lane (L_qj of lane q IS its l): taking it before the shuffled updates removes
+        // one shuffle latency per column from the critical path; same operation, same bits as the generic update below
+        if (j + 1 < d) piv = fmaf(-l, l, a[j + 1]);
+#pragma unroll
+        for (int q = j + 1; q < d; q++) a[q] = fmaf(-l, __shfl_sync(FULL, l, q), a[q]);
+    }
+    __syncwarp();
+    if (lane < d) {
+#pragma unroll
+        for (int k = 0; k < d; k++) C[k * ldc + lane] = k <= lane ? a[k] : 0.0f;
+    }
+    __syncwarp();
+}
+
 template <int NR, int SC = 0, int NEC = 0>          // SC / NEC: compile-time sample / elite counts, see k_inner_cem_fast
 __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
@@ -1210,8 +1249,8 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
         __syncthreads();
         if (cr >= 0) icf_cov_task(xc, C, ldc, ne, cr, cg);
         __syncthreads();
-        if (warp < 2) icl_chol_lookahead<d>(C, psum, warp, lane);
-        else {                                            // the other 14 warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
+        if (warp == 0) icl_chol_regs<d>(C, lane);          // (icl_chol_lookahead, two warps, was the previous version: 3.7 us per factorisation against ~1.7)
+        else if (warp >= 2) {                             // the other warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
             const float* zg = c.zb_iterT + (size_t)it * d * (S - ne);
 #pragma unroll 1
             for (int i = tid - 64; i < d * (S - ne); i += nt - 64) zs[i] = __ldg(zg + i);
