@@ -1132,18 +1132,30 @@ __device__ __forceinline__ void icl_chol_regs(float* __restrict__ C, int lane) {
         const float4 v = *reinterpret_cast<const float4*>(C + r * ldc + 4 * g);
         a[4 * g] = v.x; a[4 * g + 1] = v.y; a[4 * g + 2] = v.z; a[4 * g + 3] = v.w;
     }
-    float piv = a[0];                                      // lane j holds the pivot of column j here when column j starts
+    // Software pipeline: the NEXT column's pivot chain (shuffle -> sqrt -> reciprocal, ~85 cycles of pure latency) is started before the current column's trailing
+    // updates (25 - j shuffles + fma, ~80 cycles of issue) and runs under them.  The next pivot is lane j+1's own diagonal entry, whose update needs no other lane
+    // (L_qj of lane q IS its l): same operation, same bits as the generic update.  sqrt_rcp_fast is branch free, so chain and updates share one basic block; the
+    // out-of-range case (uniform over the warp) is patched after the updates.
+    float dd, rd;
+    {
+        const float a00 = __shfl_sync(FULL, a[0], 0);
+        if (!dm::sqrt_rcp_fast(a00, dd, rd)) { const float2 v = dm::sqrt_rcp_slow(a00); dd = v.x; rd = v.y; }
+    }
 #pragma unroll
     for (int j = 0; j < d; j++) {
-        const float ajj = __shfl_sync(FULL, piv, j);
-        float dd, rd; dm::sqrt_rcp(ajj, dd, rd);
         const float l = lane == j ? dd : a[j] * rd;        // L[r][j] (meaningful for r >= j)
         a[j] = l;
-        // the next pivot is lane j+1's own diagonal entry, whose update needs no other lane (L_qj of lane q IS its l): taking it before the shuffled updates removes
-        // one shuffle latency per column from the critical path; same operation, same bits as the generic update below
-        if (j + 1 < d) piv = fmaf(-l, l, a[j + 1]);
+        float ajn = 0.0f, ddn = 0.0f, rdn = 0.0f; bool okn = true;
+        if (j + 1 < d) {
+            ajn = __shfl_sync(FULL, fmaf(-l, l, a[j + 1]), j + 1);
+            okn = dm::sqrt_rcp_fast(ajn, ddn, rdn);
+        }
 #pragma unroll
         for (int q = j + 1; q < d; q++) a[q] = fmaf(-l, __shfl_sync(FULL, l, q), a[q]);
+        if (j + 1 < d) {
+            if (!okn) { const float2 v = dm::sqrt_rcp_slow(ajn); ddn = v.x; rdn = v.y; }
+            dd = ddn; rd = rdn;
+        }
     }
     __syncwarp();
     if (lane < d) {
@@ -1261,7 +1273,8 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
             const float* zT = zs;
 #pragma unroll 1
             for (int task = tid; task < nrow * NG; task += nt) {
-                const int g4 = task / nrow, r = task - g4 * nrow;
+                // column group g4 costs 4 g4 + 4 steps: the longest groups go to the first pass, so the (partial) second pass holds the shortest tasks
+                const int gq = task / nrow, g4 = NG - 1 - gq, r = task - gq * nrow;
                 const int kend = min(4 * g4 + 3, d - 1);
                 pk::f2 a01 = pk::dup(0.0f), a23 = pk::dup(0.0f);
 #pragma unroll 4
