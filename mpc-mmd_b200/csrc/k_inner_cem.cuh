@@ -1183,7 +1183,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
     float* ecost = sm + L.ecost; float* eb = sm + L.ebetas; int* ei = (int*)(sm + L.eidxs);
     int* tis = (int*)(sm + L.total); float* rsum = sm + L.total + al4(S);        // per-sample reduced sets (packed) and row sums, behind the shared layout
     float* zs = rsum + al4(S * NR);                                              // this iteration's resampling normals [column][row], staged while warp 0 factors
-    float* psum = zs + al4(d * (S - ne));                                        // look-ahead partial sums of the two-warp Cholesky, [2][32][4]
+    float* psum = zs + al4(d * (S - ne));                                        // look-ahead partial sums of the two-warp Cholesky, [2][32][4] (previous version; kept in the layout)
     {   // distance table of the mother features  [kernel_computation.py:31-33]; the features borrow the th region
         float* F = th;
         const float* Fg = ra.feat + (size_t)g * nm * 2 * NV;
@@ -1230,7 +1230,7 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
             idxs[s] = tis[s];
         }
         __syncthreads();
-        if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);
+        if (warp == 0) icf_select(lane, S, n_old, ne, ecost, cost, perm, ecost);      // (a CTA-wide rank count, 4 threads per candidate, was measured here: its two extra block barriers cost more than the one-warp rounds, 4.79 vs 4.71 ms)
         __syncthreads();
         float v[ICF_MAX_NE]; float mu = 0.0f, gb = 0.0f; int gi = 0;
         if (tid < d) {
@@ -1263,9 +1263,18 @@ __global__ void __launch_bounds__(ICL_THREADS, 1) k_inner_cem_lat(DCfg c, RollAr
         __syncthreads();
         if (warp == 0) icl_chol_regs<d>(C, lane);          // (icl_chol_lookahead, two warps, was the previous version: 3.7 us per factorisation against ~1.7)
         else if (warp >= 2) {                             // the other warps fetch the iteration's normals (first touch: L2 latency) behind the Cholesky
+            // eight independent loads in flight per thread, then the stores: rolled one at a time, each thread paid the L2 / DRAM latency of a first touch six times in
+            // a row (the ncu source page showed this phase waiting on these stores, not on the factorisation)
             const float* zg = c.zb_iterT + (size_t)it * d * (S - ne);
+            const int nz = d * (S - ne), st = nt - 64;
 #pragma unroll 1
-            for (int i = tid - 64; i < d * (S - ne); i += nt - 64) zs[i] = __ldg(zg + i);
+            for (int i0 = tid - 64; i0 < nz; i0 += 8 * st) {
+                float t8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) t8[u] = i0 + u * st < nz ? __ldg(zg + i0 + u * st) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (i0 + u * st < nz) zs[i0 + u * st] = t8[u];
+            }
         }
         __syncthreads();
         {   // resample: task = (new row r, group of four columns g4); columns 4 g4 .. 4 g4 + 3 take k = 0 .. 4 g4 + 3 ascending (icf_mvn_row_unrolled's order)
