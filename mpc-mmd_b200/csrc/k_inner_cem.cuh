@@ -1,11 +1,14 @@
 // k_inner_cem.cuh -- the reduced-set inner CEM of mmd_opt for num_reduced^2 + 1 <= 32 (num_reduced <= 5), the dominant
-// kernel of a solve.  Same arithmetic contract as k_inner_cem_gen (k_risk.cuh) and oracle_inner_cem (bit for bit), but
-// mapped for instruction issue, which is what bounds it (profiles/r01_v3_summary.md):
-//   * Laplace-kernel exponentials two at a time on Blackwell's packed FP32 pipe (FFMA2 / FADD2 / FMUL2, IEEE per lane),
-//   * top-num_reduced |theta| selection on packed (value | index) integer keys with min/max (exact path on near ties),
+// kernel of a solve.  Same arithmetic contract as the generic kernel (k_risk.cuh) and oracle_inner_cem (bit for bit), but
+// mapped for instruction issue, which is what bounds it (its time follows its executed instructions):
+//   * Laplace kernel entries k(d; sigma) = 2^(-(d s2)) two at a time on Blackwell's packed FP32 pipe (FFMA2 / FADD2 / FMUL2,
+//     IEEE per lane), four columns of a distance row per 16-byte shared-memory load,
+//   * top-(num_reduced + 1) |theta| selection on packed (value | index) integer keys by a min / max merge network (exact path on near ties),
 //   * elite selection by ONE warp with redux.sync min over per-lane sorted candidate lists (no O(S^2) rank count),
-//   * covariance, Cholesky (row per lane, right-looking, in registers) and the multivariate-normal resampling in
-//     packed FP32 with float4 shared-memory operands.
+//   * covariance (exact division by num_elite - 1 = 10), panel Cholesky by one warp (one range check per pivot: dm::sqrt_rcp) and the
+//     multivariate-normal resampling in packed FP32 with float4 shared-memory operands,
+//   * the reference's sample / elite counts (100 / 11) as template constants, so the shared-memory layout folds into immediate offsets.
+// Latency builds (k_inner_cem_lat, the LAT build of k_inner_cem_fast) spread a chain over up to 16 warps and factor in registers (icl_chol_regs).
 // Replaces beta_cem.compute_cem (S/compute_beta.py:93-157) + kernel_matrix.compute_kernel (S/kernel_computation.py:19-65)
 // + Costs.compute_mmd_obs / compute_mmd_lane (S/optimizer/costs.py:121-135, 173-186).
 #pragma once
