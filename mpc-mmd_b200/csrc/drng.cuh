@@ -198,41 +198,51 @@ __device__ __forceinline__ void gamma_table_fill(Key stream_key, uint32_t n, uin
     const float u = uniform01_from_bits(bits1(subkey));
     t[(size_t)10 * n] = dm::log1p_(-u);
 }
+// PF (latency regime): all eleven candidate fields are requested up front, so a replay costs ONE global-memory round trip instead of up to four dependent ones
+// (the acceptance test decides which fields it reads); the throughput kernels keep the lazy loads (most samples accept in round 0 and read five fields).
+template <bool PF = false>
 __device__ __forceinline__ float loggamma_replay(const float* __restrict__ t, size_t n, float alpha, bool& ok) {
+    float pf[GT_FIELDS];
+    if constexpr (PF) {
+#pragma unroll
+        for (int i = 0; i < GT_FIELDS; i++) pf[i] = t[(size_t)i * n];
+    }
+    auto T = [&](int i) -> float { if constexpr (PF) return pf[i]; else return t[(size_t)i * n]; };
     const float one_over_three = 0.333333343f, squeeze_const = 0.0331f;
     const bool boost_mask = alpha >= 1.0f;
     const float alpha_orig = alpha;
     alpha = boost_mask ? alpha : alpha + 1.0f;
     const float d = alpha - one_over_three;
     const float c = one_over_three / sqrtf(d);
-    float x = t[0];
+    float x = T(0);
     float v = 1.0f + x * c;
-    if (v <= 0.0f) { x = t[n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false; }
+    if (v <= 0.0f) { x = T(1); v = 1.0f + x * c; if (v <= 0.0f) ok = false; }
     float X = x * x, V = (v * v) * v, lv = dm::log_(V);
     bool cont;
-    { const float U = t[2 * n], LU = t[3 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+    { const float U = T(2), LU = T(3); const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
     if (cont) {
-        x = t[4 * n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false;
+        x = T(4); v = 1.0f + x * c; if (v <= 0.0f) ok = false;
         X = x * x; V = (v * v) * v; lv = dm::log_(V);
-        { const float U = t[5 * n], LU = t[6 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+        { const float U = T(5), LU = T(6); const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
         if (cont) {
-            x = t[7 * n]; v = 1.0f + x * c; if (v <= 0.0f) ok = false;
+            x = T(7); v = 1.0f + x * c; if (v <= 0.0f) ok = false;
             X = x * x; V = (v * v) * v; lv = dm::log_(V);
-            { const float U = t[8 * n], LU = t[9 * n]; const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
+            { const float U = T(8), LU = T(9); const float xx = squeeze_const * (X * X); cont = (U >= 1.0f - xx) && (LU >= X * 0.5f + d * ((1.0f - V) + lv)); }
             if (cont) ok = false;
         }
     }
-    const float lb = t[10 * n];
+    const float lb = T(10);
     float log_boost;
     if (boost_mask || lb == 0.0f) log_boost = 0.0f;
     else log_boost = lb * (1.0f / alpha_orig);
     return (dm::log_(d) + lv) + log_boost;
 }
 // element e of random.beta(key, a, b): tab -> [2 streams (a, b)][GT_FIELDS][n]; (ka, kb) = split(key) for the fallback
+template <bool PF = false>
 __device__ __forceinline__ float beta_replay(const float* __restrict__ tab, Key key, uint32_t n, uint32_t e, float a, float b) {
     bool oka = true, okb = true;
-    float lga = loggamma_replay(tab + e, n, a, oka);
-    float lgb = loggamma_replay(tab + (size_t)GT_FIELDS * n + e, n, b, okb);
+    float lga = loggamma_replay<PF>(tab + e, n, a, oka);
+    float lgb = loggamma_replay<PF>(tab + (size_t)GT_FIELDS * n + e, n, b, okb);
     if (!(oka && okb)) {                       // rare: more candidates needed than the table holds
         Key ka, kb; split2(key, ka, kb);
         if (!oka) lga = loggamma_one(split_row(ka, n, e), a);

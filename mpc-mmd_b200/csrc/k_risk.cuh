@@ -186,7 +186,7 @@ __host__ __device__ inline int roll_smem_floats(int spb, int nr, int np, int R, 
 // NZ = the noise path the launch needs, fixed at compile time so that a kernel carries only that path's code and registers: 0 Gaussian, 1 Beta draws replayed from the
 // per-episode candidate table (every beta-noise solve), 2 decided at run time (injected draws / direct sampler of the stage entry points)
 enum { NZ_GAUSS = 0, NZ_BETA_TABLE = 1, NZ_ANY = 2 };
-template <int NZ = NZ_ANY>
+template <int NZ = NZ_ANY, bool PF = false>
 __device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, int g, int e, int el, int t, int n, float& an, float& sn) {
     const float av = a.acc[(size_t)g * T_ + t], sv = a.steer[(size_t)g * T_ + t];
     const float* z3 = a.z3 + e * a.z_stride;
@@ -202,8 +202,8 @@ __device__ __forceinline__ void noisy_control(const DCfg& c, const RiskArgs& a, 
             b1 = a.binj1[(size_t)g * n + el]; b2 = a.binj2[(size_t)g * n + el];
         } else if (NZ == NZ_BETA_TABLE || a.btab) {
             const float* bt = a.btab + e * a.btab_stride;
-            b1 = dr::beta_replay(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
-            b2 = dr::beta_replay(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
+            b1 = dr::beta_replay<PF>(bt, k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
+            b2 = dr::beta_replay<PF>(bt + (size_t)2 * GT_FIELDS * n, k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
         } else {
             b1 = dr::beta_elem(k1, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(av), c.beta_b * fabsf(av));
             b2 = dr::beta_elem(k2, (uint32_t)n, (uint32_t)el, c.beta_a * fabsf(sv), c.beta_b * fabsf(sv));
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
-            float an, sn; noisy_control<NZ>(c, a, g, g / a.B, el, el % np, n, an, sn);
+            float an, sn; noisy_control<NZ, OV == OV_FOLD>(c, a, g, g / a.B, el, el % np, n, an, sn);      // latency regime: prefetching replay
             const float tn = dm::tan_(sn);                     // the rollouts (and k_opt_risk's re-rolls) only ever need tan(steer)
             sm[ls * 2 * n + el] = an; sm[ls * 2 * n + n + el] = tn;
             ra.ctrl[(size_t)g * 2 * n + el] = an; ra.ctrl[(size_t)g * 2 * n + n + el] = tn;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) k_rollouts(DCfg c, RollArgs ra) 
 #pragma unroll 1
         for (int i = tid; i < ns * n; i += nt) {
             const int ls = i / n, el = i % n, g = g0 + ls;
-            float an, sn; noisy_control<NZ>(c, a, g, g / a.B, el, el % np, n, an, sn);
+            float an, sn; noisy_control<NZ, true>(c, a, g, g / a.B, el, el % np, n, an, sn);      // latency regime: prefetching replay
             sm[ls * per + 4 * tail + el] = an; sm[ls * per + 4 * tail + n + el] = dm::tan_(sn);
         }
         __syncthreads();
