@@ -605,7 +605,8 @@ __device__ __forceinline__ long long sort_key64(float x, int idx) {
     return ((long long)k << 12) | (long long)idx;
 }
 
-template <int NR>
+// SC / NEC: compile-time copies of the inner CEM's sample / elite counts (0 = from the configuration), as in k_inner_cem_fast: the shared-memory layout folds
+template <int NR, int SC = 0, int NEC = 0>
 __global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_cem(DCfg c, RollArgs ra) {
     extern __shared__ __align__(128) float sm[];
     const RiskArgs& a = ra.r;
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(risko_threads(NR), (NR <= 5) ? 7 : 1) k_inner_
     constexpr bool SMALL = d <= 32;
     constexpr int nt = risko_threads(NR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e = g / a.B, np = c.np, S = c.S_in, ne = c.n_el_in;
+    const int e = g / a.B, np = c.np, S = SC ? SC : c.S_in, ne = NEC ? NEC : c.n_el_in;
     const OptLayout L = opt_layout(NR, np, S, ne);
     const int ldc = L.ldc;
     float* F = sm + L.F; float* D = sm + L.D; float* small = sm + L.small;

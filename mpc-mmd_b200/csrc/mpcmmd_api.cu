@@ -236,6 +236,10 @@ static inner_cem_fn inner_cem_kernel(const DCfg& d, int kind) {
     if (kind == INNER_CTA_LAT) switch (d.nr) {
         case 2: return k_inner_cem_fast<2, true>; case 3: return k_inner_cem_fast<3, true>; case 4: return k_inner_cem_fast<4, true>; case 5: return k_inner_cem_fast<5, true>;
     }
+    if (d.S_in == 100 && d.n_el_in == 11) switch (d.nr) {       // the reference's sizes as compile-time constants (generic kernel, num_reduced 6..10)
+        case 6: return k_inner_cem<6, 100, 11>; case 7: return k_inner_cem<7, 100, 11>; case 8: return k_inner_cem<8, 100, 11>;
+        case 9: return k_inner_cem<9, 100, 11>; case 10: return k_inner_cem<10, 100, 11>;
+    }
     switch (d.nr) {
         case 2: return k_inner_cem<2>;
         case 3: return k_inner_cem<3>;

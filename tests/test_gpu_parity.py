@@ -281,6 +281,28 @@ def test_stage_risk_bit_exact(mods, cost, noise, nr, npr, nobs):
     assert np.any(got["risk"] != got["risk"][0]) or cost == "saa"
 
 
+@pytest.mark.parametrize("nr,npr,noise", [(6, 20, "gaussian"), (10, 30, "beta")])
+def test_stage_risk_generic_kernel_reference_sizes(mods, nr, npr, noise):
+    """num_reduced 6..10 with the reference's inner-CEM population (100 samples, 11 elites): the generic shared-memory kernel in its build with those sizes as
+    compile-time constants (k_inner_cem<NR, 100, 11>); the other generic-kernel cases run reduced populations, i.e. the run-time-size build.  Bit exact vs the oracle."""
+    cem_impl, O = mods
+    prob, ora = _pair(mods, (nr, 2, 0.3 if noise == "beta" else 0.1, npr, noise, 0.05, 0.01), maxiter_beta_cem=3)
+    rng = np.random.default_rng(23)
+    n = 3
+    acc, steer = _controls(ora, rng, n)
+    st0 = np.array([0.0, 1.75, 5.0, 0.0, 0.0], f32)
+    noise_t = ora.noise_tables(777, 2)
+    sc = __import__("oracle.oracle", fromlist=["x"]).static_scene(2, 4)
+    xo, yo, _ = ora.compute_obs_trajectories(*sc)
+    xo = xo.copy(); xo[0] = np.linspace(2, 60, 100)
+    yo = yo.copy(); yo[0] = 1.75
+    got = prob.stage_risk("mmd_opt", acc, steer, st0, noise_t, xo, yo)
+    for i in range(n):
+        ref = ora.risk("mmd_opt", acc[i], steer[i], st0, noise_t, xo, yo)
+        for k in ("risk", "lane", "beta", "sigma", "res_beta"):
+            _eq(got[k][i], ref[k], f"nr={nr} {k}[{i}]")
+
+
 @pytest.mark.parametrize("cost,nr,npr", [("cvar", 5, 50), ("mmd_opt", 5, 30), ("mmd_random", 4, 20)])
 def test_stage_risk_injected_beta_draws(mods, cost, nr, npr):
     """beta noise with the two jax.random.beta samples of cem_helper.py:427-436 INJECTED as tensors (mpcmmd_stage_risk_injected): no device RNG
