@@ -96,6 +96,20 @@ def test_oracle_laplace_kernel_entry_accuracy(O):
     assert np.isnan(O.math_vec("lap", np.array([np.nan, 1.0], f32), np.array([1.0, np.nan], f32))).all()
 
 
+def test_topk_merge_network_model():
+    """the min / max network of the kernel's top-(num_reduced + 1) selection (tools/topk_network.py is its executable description): the 7-exchange merger sorts every
+    reachable 0-1 pattern of the half-cleaned sequence, no 6-exchange network does, and the whole routine equals sorting on random key sets"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("topk_network", os.path.join(ROOT, "tools", "topk_network.py"))
+    tn = importlib.util.module_from_spec(spec); spec.loader.exec_module(tn)
+    pats = frozenset(tn.reachable_patterns())
+    for c in tn.MERGER:
+        pats = tn.apply(c, pats)
+    assert all(tn.is_sorted(p) for p in pats)
+    assert len(tn.shortest_network()) == len(tn.MERGER) == 7
+    assert tn.check(5000)
+
+
 def test_oracle_math_special_values(O):
     assert O.math_vec("exp", np.array([-1000.0], f32))[0] == O.math_vec("exp", np.array([-87.0], f32))[0] > 0      # clamp, part of the contract
     assert np.isneginf(O.math_vec("log", np.array([0.0], f32))[0]) and np.isnan(O.math_vec("log", np.array([-1.0], f32))[0])
