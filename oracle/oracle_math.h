@@ -47,7 +47,7 @@ static inline float om_exp(float x) {
  * DESIGN.md section 3, D1 -- restated, csrc/dmath.cuh dm::lap_ is the same operations):
  *   per bandwidth: rinv = 1 / sigma, s2 = rinv * log2(e), dcap = 125 / s2;
  *   per distance:  dc = min(d, dcap) (NaN propagates), t = fma(dc, -s2, MAGIC), n = bits(t) - bits(MAGIC), f = fma(dc, -s2, MAGIC - t) in [-1/2, 1/2],
- *                  p = P6(f) ~ 2^f (degree-6 minimax, constant term 1), k = p * 2^n.  <= 1 ulp of 2^(-(d s2)); k(0) = 1 exactly. */
+ *                  p = P6(f) ~ 2^f (degree 6, constant term 1, interpolating 2^f at the Chebyshev extrema of the interval: tools/lap_poly.py), k = p * 2^n.  <= 1 ulp of 2^(-(d s2)); k(0) = 1 exactly. */
 typedef struct { float ns2, dcap; } om_lapscale_t;
 static inline om_lapscale_t om_lap_scale(float sigma) {
     float rinv = 1.0f / sigma;

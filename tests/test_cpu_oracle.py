@@ -96,6 +96,25 @@ def test_oracle_laplace_kernel_entry_accuracy(O):
     assert np.isnan(O.math_vec("lap", np.array([np.nan, 1.0], f32), np.array([1.0, np.nan], f32))).all()
 
 
+def test_laplace_polynomial_coefficients_are_reproducible():
+    """the six constants of om_lap / dm::lap_ are the float32 roundings of the degree-6 polynomial with constant term 1 that interpolates 2^f at the Chebyshev
+    extrema of [-1/2, 1/2] (tools/lap_poly.py re-derives them), in BOTH sources"""
+    import importlib.util, re
+    spec = importlib.util.spec_from_file_location("lap_poly", os.path.join(ROOT, "tools", "lap_poly.py"))
+    lp = importlib.util.module_from_spec(spec); spec.loader.exec_module(lp)
+    c, emax, _ = lp.levelled_exp2()
+    assert emax < 5e-9
+    want = [np.float32(v) for v in c]
+    ora = open(os.path.join(ROOT, "oracle", "oracle_math.h")).read()
+    body = ora[ora.index("static inline float om_lap(float d"):]
+    lits = [np.float32(float(m)) for m in re.findall(r"([0-9]\.[0-9]{8,})f", body[:body.index("return p *")])]
+    assert lits == want[::-1]                                            # Horner order: c6 first
+    dev = open(os.path.join(ROOT, "mpc-mmd_b200", "csrc", "dmath.cuh")).read()
+    for j, v in enumerate(want, 1):
+        m = re.search(r"#define DM_LAP_C%d ([0-9.e-]+)f" % j, dev)
+        assert m and np.float32(float(m.group(1))) == v
+
+
 def test_topk_merge_network_model():
     """the min / max network of the kernel's top-(num_reduced + 1) selection (tools/topk_network.py is its executable description): the 7-exchange merger sorts every
     reachable 0-1 pattern of the half-cleaned sequence, no 6-exchange network does, and the whole routine equals sorting on random key sets"""
